@@ -1,0 +1,318 @@
+// fsb200 — HBM-bound pointwise / gather kernels of the step. All bf16 I/O with fp32 math, 16-byte vector accesses,
+// grid-stride loops with grid = k * #SMs.
+//   rope        : layers/positional_embeddings.py:71-87 (rotate_half convention) applied in place to the q and k
+//                 slices of the packed QKV projection output (layers/transformer.py:488-523)
+//   swiglu      : LLaMAParallelMLP.forward layers/transformer.py:620-623  silu(w1 x) * (w3 x)
+//   gated gelu  : MT5DenseGatedActDense (transformers mt5/modeling_mt5.py:96-123)  gelu_new(wi_0 x) * (wi_1 x)
+//   gelu fwd/bwd: layers/activations.py:60-94 (tanh form, hand-written backward) and :98-117 (erf form)
+//   embedding   : VocabParallelEmbedding.forward mpu/layers.py:104-130 (+ learned position / token-type rows for
+//                 BERT / GPT-2: transformers bert/modeling_bert.py:53-112, gpt2/modeling_gpt2.py wte+wpe)
+//   add         : residual adds layers/transformer.py:775-788
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace fsb {
+
+static int ew_grid(int64_t work_items, int threads) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  int64_t cap = int64_t(num_sms()) * 16;
+  return int(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------- rope
+// x: rows of `nheads` heads; head h of row t starts at x + t*row_stride + h*head_stride (elements); head_dim D.
+// Rotates D/2 pairs (d, d+D/2): out_d = x_d cos - sign*x_{d+D/2} sin ; out_{d+D/2} = x_{d+D/2} cos + sign*x_d sin.
+// cos/sin: fp32 tables [max_pos, D/2]; pos[t] int64 (position_ids flattened to rows).  sign=+1 fwd, -1 bwd.
+__global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ cos_t,
+                                                   const float* __restrict__ sin_t, const int64_t* __restrict__ pos,
+                                                   int64_t rows, int nheads, int D, int64_t row_stride,
+                                                   int64_t head_stride, float sign) {
+  const int half = D >> 1;
+  const int vec_per_head = half >> 3;  // 8 pairs per thread-iteration
+  const int64_t total = rows * nheads * vec_per_head;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int v = int(i % vec_per_head);
+    const int64_t th = i / vec_per_head;
+    const int h = int(th % nheads);
+    const int64_t t = th / nheads;
+    const int64_t p = pos[t];
+    __nv_bfloat16* base = x + t * row_stride + h * head_stride + v * 8;
+    float a[8], b[8], c[8], s[8];
+    unpack8(*reinterpret_cast<const uint4*>(base), a);
+    unpack8(*reinterpret_cast<const uint4*>(base + half), b);
+    const float4* cp = reinterpret_cast<const float4*>(cos_t + p * half + v * 8);
+    const float4* sp = reinterpret_cast<const float4*>(sin_t + p * half + v * 8);
+    float4 c0 = cp[0], c1 = cp[1], s0 = sp[0], s1 = sp[1];
+    c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+    s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+    float oa[8], ob[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      oa[j] = a[j] * c[j] - sign * b[j] * s[j];
+      ob[j] = b[j] * c[j] + sign * a[j] * s[j];
+    }
+    *reinterpret_cast<uint4*>(base) = pack8(oa);
+    *reinterpret_cast<uint4*>(base + half) = pack8(ob);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- gated activations
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + __expf(-x)); }
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.f + tanhf(k0 * x * (1.f + k1 * x * x)));
+}
+__device__ __forceinline__ float dgelu_tanh_f(float x) {
+  // activations.py:70-77 bias_gelu_back
+  const float t = tanhf(0.79788456f * x * (1.f + 0.044715f * x * x));
+  return 0.5f * x * ((1.f - t * t) * (0.79788456f + 0.1070322243f * x * x)) + 0.5f * (1.f + t);
+}
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+__device__ __forceinline__ float dgelu_erf_f(float x) {
+  return 0.5f * (1.f + erff(x * 0.7071067811865476f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+// act: 0 silu, 1 gelu_tanh, 2 gelu_erf
+template <int ACT>
+__device__ __forceinline__ float act_f(float x) {
+  if (ACT == 0) return x * sigmoid_f(x);
+  if (ACT == 1) return gelu_tanh_f(x);
+  return gelu_erf_f(x);
+}
+template <int ACT>
+__device__ __forceinline__ float dact_f(float x) {
+  if (ACT == 0) { float s = sigmoid_f(x); return s * (1.f + x * (1.f - s)); }
+  if (ACT == 1) return dgelu_tanh_f(x);
+  return dgelu_erf_f(x);
+}
+
+// out[t, c] = act(gate[t, c]) * up[t, c]; gate/up/out have independent row strides (elements).
+template <int ACT>
+__global__ void __launch_bounds__(256) glu_fwd_kernel(const __nv_bfloat16* __restrict__ gate,
+                                                      const __nv_bfloat16* __restrict__ up,
+                                                      __nv_bfloat16* __restrict__ out, int64_t rows, int cols,
+                                                      int64_t ld_gate, int64_t ld_up, int64_t ld_out) {
+  const int vpr = cols >> 3;
+  const int64_t total = rows * vpr;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t t = i / vpr;
+    const int c = int(i % vpr) * 8;
+    float g[8], u[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(gate + t * ld_gate + c), g);
+    unpack8(*reinterpret_cast<const uint4*>(up + t * ld_up + c), u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = act_f<ACT>(g[j]) * u[j];
+    *reinterpret_cast<uint4*>(out + t * ld_out + c) = pack8(o);
+  }
+}
+template <int ACT>
+__global__ void __launch_bounds__(256) glu_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                      const __nv_bfloat16* __restrict__ gate,
+                                                      const __nv_bfloat16* __restrict__ up,
+                                                      __nv_bfloat16* __restrict__ dgate, __nv_bfloat16* __restrict__ dup,
+                                                      int64_t rows, int cols, int64_t ld_dout, int64_t ld_gate,
+                                                      int64_t ld_up, int64_t ld_dgate, int64_t ld_dup) {
+  const int vpr = cols >> 3;
+  const int64_t total = rows * vpr;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t t = i / vpr;
+    const int c = int(i % vpr) * 8;
+    float d[8], g[8], u[8], og[8], ou[8];
+    unpack8(*reinterpret_cast<const uint4*>(dout + t * ld_dout + c), d);
+    unpack8(*reinterpret_cast<const uint4*>(gate + t * ld_gate + c), g);
+    unpack8(*reinterpret_cast<const uint4*>(up + t * ld_up + c), u);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      og[j] = d[j] * u[j] * dact_f<ACT>(g[j]);
+      ou[j] = d[j] * act_f<ACT>(g[j]);
+    }
+    *reinterpret_cast<uint4*>(dgate + t * ld_dgate + c) = pack8(og);
+    *reinterpret_cast<uint4*>(dup + t * ld_dup + c) = pack8(ou);
+  }
+}
+
+// Plain activation: y = act(x) ; backward dx = dy * act'(x). Contiguous [n] (n % 8 == 0).
+template <int ACT>
+__global__ void __launch_bounds__(256) act_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t nvec) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nvec; i += int64_t(gridDim.x) * blockDim.x) {
+    float a[8], o[8];
+    unpack8(x[i], a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = act_f<ACT>(a[j]);
+    y[i] = pack8(o);
+  }
+}
+template <int ACT>
+__global__ void __launch_bounds__(256) act_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x,
+                                                      uint4* __restrict__ dx, int64_t nvec) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nvec; i += int64_t(gridDim.x) * blockDim.x) {
+    float a[8], d[8], o[8];
+    unpack8(x[i], a);
+    unpack8(dy[i], d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = d[j] * dact_f<ACT>(a[j]);
+    dx[i] = pack8(o);
+  }
+}
+
+// out = a + b (bf16, contiguous)
+__global__ void __launch_bounds__(256) add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b,
+                                                  uint4* __restrict__ out, int64_t nvec) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nvec; i += int64_t(gridDim.x) * blockDim.x) {
+    float x[8], y[8], o[8];
+    unpack8(a[i], x);
+    unpack8(b[i], y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = x[j] + y[j];
+    out[i] = pack8(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- embedding
+// out[t] = W[ids[t]] (+ P[pos[t]]) (+ T[tt[t]]);   pos == nullptr with P != nullptr means pos[t] = t % seq_len.
+__global__ void __launch_bounds__(256) embedding_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ pos,
+                                                            const int64_t* __restrict__ tt,
+                                                            const __nv_bfloat16* __restrict__ W,
+                                                            const __nv_bfloat16* __restrict__ P,
+                                                            const __nv_bfloat16* __restrict__ T,
+                                                            __nv_bfloat16* __restrict__ out, int64_t rows, int cols,
+                                                            int seq_len) {
+  const int vpr = cols >> 3;
+  const int64_t total = rows * vpr;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t t = i / vpr;
+    const int c = int(i % vpr) * 8;
+    float o[8];
+    unpack8(*reinterpret_cast<const uint4*>(W + ids[t] * cols + c), o);
+    if (P != nullptr) {
+      const int64_t p = pos ? pos[t] : (t % seq_len);
+      float a[8];
+      unpack8(*reinterpret_cast<const uint4*>(P + p * cols + c), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += a[j];
+    }
+    if (T != nullptr) {
+      float a[8];
+      unpack8(*reinterpret_cast<const uint4*>(T + (tt ? tt[t] : 0) * cols + c), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += a[j];
+    }
+    *reinterpret_cast<uint4*>(out + t * cols + c) = pack8(o);
+  }
+}
+// dW[ids[t]] += dout[t]  (bf16x2 reductions at L2; rows hit by several tokens accumulate there)
+__global__ void __launch_bounds__(256) embedding_bwd_kernel(const int64_t* __restrict__ ids,
+                                                            const __nv_bfloat16* __restrict__ dout,
+                                                            __nv_bfloat16* __restrict__ dW, int64_t rows, int cols,
+                                                            int64_t idx_mod) {
+  const int vpr = cols >> 3;
+  const int64_t total = rows * vpr;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t t = i / vpr;
+    const int c = int(i % vpr) * 8;
+    const int64_t r = ids ? ids[t] : (t % idx_mod);
+    const uint4 q = *reinterpret_cast<const uint4*>(dout + t * cols + c);
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(dW + r * cols + c);
+    atomicAdd(dst + 0, *reinterpret_cast<const __nv_bfloat162*>(&q.x));
+    atomicAdd(dst + 1, *reinterpret_cast<const __nv_bfloat162*>(&q.y));
+    atomicAdd(dst + 2, *reinterpret_cast<const __nv_bfloat162*>(&q.z));
+    atomicAdd(dst + 3, *reinterpret_cast<const __nv_bfloat162*>(&q.w));
+  }
+}
+
+}  // namespace fsb
+
+using namespace fsb;
+
+extern "C" int fsb_rope_inplace(void* x, const float* cos_table, const float* sin_table, const int64_t* positions,
+                                int64_t rows, int nheads, int head_dim, int64_t row_stride, int64_t head_stride,
+                                int64_t max_pos, int backward, fsb_stream_t st) {
+  FSB_REQUIRE(x && cos_table && sin_table && positions, "rope: null pointer");
+  FSB_REQUIRE(rows > 0 && nheads > 0 && head_dim % 16 == 0 && head_dim > 0, "rope: head_dim must be a multiple of 16");
+  FSB_REQUIRE(row_stride % 8 == 0 && head_stride % 8 == 0 && aligned16(x) && aligned16(cos_table) && aligned16(sin_table),
+              "rope: alignment");
+  (void)max_pos;
+  const int64_t total = rows * nheads * (head_dim / 16);
+  rope_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)st>>>((__nv_bfloat16*)x, cos_table, sin_table, positions, rows,
+                                                               nheads, head_dim, row_stride, head_stride,
+                                                               backward ? -1.f : 1.f);
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+
+extern "C" int fsb_glu_fwd(int act, const void* gate, const void* up, void* out, int64_t rows, int64_t cols,
+                           int64_t ld_gate, int64_t ld_up, int64_t ld_out, fsb_stream_t st) {
+  FSB_REQUIRE(act >= 0 && act <= 2, "glu_fwd: bad act %d", act);
+  FSB_REQUIRE(gate && up && out && rows > 0 && cols > 0 && cols % 8 == 0, "glu_fwd: bad args");
+  FSB_REQUIRE(ld_gate % 8 == 0 && ld_up % 8 == 0 && ld_out % 8 == 0 && aligned16(gate) && aligned16(up) && aligned16(out),
+              "glu_fwd: alignment");
+  const int g = ew_grid(rows * (cols / 8), 256);
+#define L(A) glu_fwd_kernel<A><<<g, 256, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, \
+                                                               (__nv_bfloat16*)out, rows, int(cols), ld_gate, ld_up, ld_out)
+  if (act == 0) L(0); else if (act == 1) L(1); else L(2);
+#undef L
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+extern "C" int fsb_glu_bwd(int act, const void* dout, const void* gate, const void* up, void* dgate, void* dup,
+                           int64_t rows, int64_t cols, int64_t ld_dout, int64_t ld_gate, int64_t ld_up,
+                           int64_t ld_dgate, int64_t ld_dup, fsb_stream_t st) {
+  FSB_REQUIRE(act >= 0 && act <= 2, "glu_bwd: bad act %d", act);
+  FSB_REQUIRE(dout && gate && up && dgate && dup && rows > 0 && cols > 0 && cols % 8 == 0, "glu_bwd: bad args");
+  FSB_REQUIRE((ld_dout | ld_gate | ld_up | ld_dgate | ld_dup) % 8 == 0 && aligned16(dout) && aligned16(gate) &&
+                  aligned16(up) && aligned16(dgate) && aligned16(dup),
+              "glu_bwd: alignment");
+  const int g = ew_grid(rows * (cols / 8), 256);
+#define L(A) glu_bwd_kernel<A><<<g, 256, 0, (cudaStream_t)st>>>(                                                    \
+      (const __nv_bfloat16*)dout, (const __nv_bfloat16*)gate, (const __nv_bfloat16*)up, (__nv_bfloat16*)dgate,       \
+      (__nv_bfloat16*)dup, rows, int(cols), ld_dout, ld_gate, ld_up, ld_dgate, ld_dup)
+  if (act == 0) L(0); else if (act == 1) L(1); else L(2);
+#undef L
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+extern "C" int fsb_act_fwd(int act, const void* x, void* y, int64_t n, fsb_stream_t st) {
+  FSB_REQUIRE(act >= 0 && act <= 2 && x && y && n > 0 && n % 8 == 0 && aligned16(x) && aligned16(y), "act_fwd: bad args");
+  const int g = ew_grid(n / 8, 256);
+#define L(A) act_fwd_kernel<A><<<g, 256, 0, (cudaStream_t)st>>>((const uint4*)x, (uint4*)y, n / 8)
+  if (act == 0) L(0); else if (act == 1) L(1); else L(2);
+#undef L
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+extern "C" int fsb_act_bwd(int act, const void* dy, const void* x, void* dx, int64_t n, fsb_stream_t st) {
+  FSB_REQUIRE(act >= 0 && act <= 2 && dy && x && dx && n > 0 && n % 8 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx),
+              "act_bwd: bad args");
+  const int g = ew_grid(n / 8, 256);
+#define L(A) act_bwd_kernel<A><<<g, 256, 0, (cudaStream_t)st>>>((const uint4*)dy, (const uint4*)x, (uint4*)dx, n / 8)
+  if (act == 0) L(0); else if (act == 1) L(1); else L(2);
+#undef L
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+extern "C" int fsb_add(const void* a, const void* b, void* out, int64_t n, fsb_stream_t st) {
+  FSB_REQUIRE(a && b && out && n > 0 && n % 8 == 0 && aligned16(a) && aligned16(b) && aligned16(out), "add: bad args");
+  add_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, n / 8);
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+extern "C" int fsb_embedding_fwd(const int64_t* ids, const int64_t* pos, const int64_t* token_type, const void* W,
+                                 const void* P, const void* T, void* out, int64_t rows, int64_t cols, int64_t seq_len,
+                                 fsb_stream_t st) {
+  FSB_REQUIRE(ids && W && out && rows > 0 && cols > 0 && cols % 8 == 0 && seq_len > 0, "embedding_fwd: bad args");
+  FSB_REQUIRE(aligned16(W) && aligned16(P) && aligned16(T) && aligned16(out), "embedding_fwd: alignment");
+  embedding_fwd_kernel<<<ew_grid(rows * (cols / 8), 256), 256, 0, (cudaStream_t)st>>>(
+      ids, pos, token_type, (const __nv_bfloat16*)W, (const __nv_bfloat16*)P, (const __nv_bfloat16*)T,
+      (__nv_bfloat16*)out, rows, int(cols), int(seq_len));
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+extern "C" int fsb_embedding_bwd(const int64_t* ids, const void* dout, void* dW, int64_t rows, int64_t cols,
+                                 int64_t idx_mod, fsb_stream_t st) {
+  FSB_REQUIRE(dout && dW && rows > 0 && cols > 0 && cols % 8 == 0, "embedding_bwd: bad args");
+  FSB_REQUIRE(ids != nullptr || idx_mod > 0, "embedding_bwd: need ids or idx_mod");
+  FSB_REQUIRE(aligned16(dout) && aligned16(dW), "embedding_bwd: alignment");
+  embedding_bwd_kernel<<<ew_grid(rows * (cols / 8), 256), 256, 0, (cudaStream_t)st>>>(
+      ids, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dW, rows, int(cols), idx_mod);
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}

@@ -1,0 +1,368 @@
+// fsb200 — persistent, warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem -> tcgen05.mma -> TMEM
+// -> epilogue warps -> HBM. Replaces the cuBLAS calls behind F.linear on the reference hot path
+// (fengshen/models/megatron/mpu/layers.py:347-360, :451-470; layers/transformer.py:136-172) and their autograd
+// transposes. One kernel, three operand layouts:
+//   NT  D = A[M,K] B[N,K]^T   both operands K-major          (forward)
+//   NN  D = A[M,K] B[K,N]     B is MN-major in shared memory  (dgrad)
+//   TN  D = A[K,M]^T B[K,N]   A and B MN-major                (wgrad)
+// MN-major tiles are fetched as 64(mn) x 64(k) TMA boxes; the UMMA descriptor's leading-byte-offset walks the boxes.
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
+// (TMEM lane quadrant = warp_id % 4). Two TMEM accumulator stages let the epilogue of tile i overlap the
+// main loop of tile i+1. Grid = min(#tiles, #SMs); static round-robin tile order, grouped 8 m-tiles deep for L2.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace fsb {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_GROUP_M = 8;
+
+struct GemmParams {
+  void* D;
+  void* aux;
+  const void* bias;
+  int64_t ldd, ldaux, stride_d, stride_aux;
+  int M, N, K, batch;
+  int d_f32;       // D dtype: 0 bf16, 1 fp32
+  int bias_f32;    // bias dtype
+  int epilogue;    // fsb_gemm_epilogue
+  int accumulate;  // D += result
+  int tiles_m, tiles_n;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024 /*align slack*/;
+};
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * x * (1.f + k1 * x * x);
+  return 0.5f * x * (1.f + tanhf(u));
+}
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& b, int& m_idx, int& n_idx) {
+  const int per = tiles_m * tiles_n;
+  b = t / per;
+  int r = t - b * per;
+  const int group_span = GEMM_GROUP_M * tiles_n;
+  const int g = r / group_span;
+  const int first_m = g * GEMM_GROUP_M;
+  const int gsize = min(tiles_m - first_m, GEMM_GROUP_M);
+  const int in_g = r - g * group_span;
+  m_idx = first_m + in_g % gsize;
+  n_idx = in_g / gsize;
+}
+
+template <int kLayout, int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const GemmParams p) {
+  constexpr bool A_MN = (kLayout == FSB_GEMM_TN);
+  constexpr bool B_MN = (kLayout != FSB_GEMM_NT);
+  using S = GemmSmem<BN>;
+  constexpr int STAGES = S::STAGES;
+  constexpr uint32_t IDESC = make_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  constexpr int TMEM_COLS = 2 * BN;  // 512 or 256
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n * p.batch;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int b, m_idx, n_idx;
+        tile_coords(t, p.tiles_m, p.tiles_n, b, m_idx, n_idx);
+        const int m0 = m_idx * GEMM_BM, n0 = n_idx * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          const int k0 = kb * GEMM_BK;
+          if constexpr (!A_MN) {
+            tma_load_3d(sa, &tmA, &full_bar[stage], k0, m0, b);
+          } else {
+#pragma unroll
+            for (int c = 0; c < GEMM_BM / 64; ++c)
+              tma_load_3d(sa + c * (GEMM_BK * 128), &tmA, &full_bar[stage], m0 + c * 64, k0, b);
+          }
+          if constexpr (!B_MN) {
+            tma_load_3d(sb, &tmB, &full_bar[stage], k0, n0, b);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_3d(sb + c * (GEMM_BK * 128), &tmB, &full_bar[stage], n0 + c * 64, k0, b);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, GEMM_BK * 128, 1024)
+                                     : make_smem_desc_sw128(sa + k * 32, 0, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, GEMM_BK * 128, 1024)
+                                     : make_smem_desc_sw128(sb + k * 32, 0, 1024);
+            umma_bf16(d_tmem, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int b, m_idx, n_idx;
+      tile_coords(t, p.tiles_m, p.tiles_n, b, m_idx, n_idx);
+      const int row = m_idx * GEMM_BM + quad * 32 + lane;
+      const int n0 = n_idx * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BN + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full_cols = (col0 + 32 <= p.N);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (full_cols || col0 + j < p.N) {
+              float bv = p.bias_f32 ? __ldg(reinterpret_cast<const float*>(p.bias) + col0 + j)
+                                    : __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0 + j));
+              v[j] += bv;
+            }
+          }
+        }
+        if (p.aux != nullptr && row_ok) {  // pre-activation copy (bf16)
+          __nv_bfloat16* ap = reinterpret_cast<__nv_bfloat16*>(p.aux) + int64_t(b) * p.stride_aux +
+                              int64_t(row) * p.ldaux + col0;
+          if (full_cols) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q;
+              q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(ap + j) = q;
+            }
+          } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) ap[j] = __float2bfloat16(v[j]);
+          }
+        }
+        if (p.epilogue == FSB_EPI_GELU_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(v[j]);
+        } else if (p.epilogue == FSB_EPI_GELU_ERF) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
+        }
+        if (row_ok) {
+          if (p.d_f32) {
+            float* dp = reinterpret_cast<float*>(p.D) + int64_t(b) * p.stride_d + int64_t(row) * p.ldd + col0;
+            if (full_cols) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 q = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (p.accumulate) {
+                  float4 o = *reinterpret_cast<const float4*>(dp + j);
+                  q.x += o.x; q.y += o.y; q.z += o.z; q.w += o.w;
+                }
+                *reinterpret_cast<float4*>(dp + j) = q;
+              }
+            } else {
+              for (int j = 0; j < 32 && col0 + j < p.N; ++j) dp[j] = p.accumulate ? dp[j] + v[j] : v[j];
+            }
+          } else {
+            __nv_bfloat16* dp =
+                reinterpret_cast<__nv_bfloat16*>(p.D) + int64_t(b) * p.stride_d + int64_t(row) * p.ldd + col0;
+            if (full_cols) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (p.accumulate) {
+                  uint4 o = *reinterpret_cast<const uint4*>(dp + j);
+                  v[j] += bf16lo(o.x); v[j + 1] += bf16hi(o.x); v[j + 2] += bf16lo(o.y); v[j + 3] += bf16hi(o.y);
+                  v[j + 4] += bf16lo(o.z); v[j + 5] += bf16hi(o.z); v[j + 6] += bf16lo(o.w); v[j + 7] += bf16hi(o.w);
+                }
+                uint4 q;
+                q.x = pack_bf16x2(v[j], v[j + 1]); q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+                q.z = pack_bf16x2(v[j + 4], v[j + 5]); q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+                *reinterpret_cast<uint4*>(dp + j) = q;
+              }
+            } else {
+              for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
+                float o = p.accumulate ? __bfloat162float(dp[j]) : 0.f;
+                dp[j] = __float2bfloat16(v[j] + o);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int kLayout, int BN>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  static bool configured = false;
+  auto kern = gemm_bf16_kernel<kLayout, BN>;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e != cudaSuccess) {
+      set_error("gemm: cudaFuncSetAttribute(%d B smem) failed: %s", S::TOTAL, cudaGetErrorString(e));
+      return FSB_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int num_tiles = p.tiles_m * p.tiles_n * p.batch;
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+
+}  // namespace fsb
+
+using namespace fsb;
+
+extern "C" int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                             int64_t ldb, void* D, int64_t ldd, int d_dtype, const void* bias, int bias_dtype,
+                             int epilogue, int accumulate, void* aux, int64_t ldaux, int64_t batch, int64_t stride_a,
+                             int64_t stride_b, int64_t stride_d, int64_t stride_aux, fsb_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  FSB_REQUIRE(layout >= 0 && layout <= 2, "gemm: bad layout %d", layout);
+  FSB_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "gemm: non-positive dims M=%ld N=%ld K=%ld batch=%ld", (long)M,
+              (long)N, (long)K, (long)batch);
+  FSB_REQUIRE(M < (1 << 30) && N < (1 << 30) && K < (1 << 30), "gemm: dims too large");
+  FSB_REQUIRE(A && B && D, "gemm: null operand");
+  FSB_REQUIRE(aligned16(A) && aligned16(B) && aligned16(D), "gemm: operands must be 16-byte aligned");
+  FSB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 (lda=%ld ldb=%ld)", (long)lda,
+              (long)ldb);
+  FSB_REQUIRE(d_dtype == FSB_BF16 || d_dtype == FSB_F32, "gemm: bad d_dtype");
+  FSB_REQUIRE(ldd % (d_dtype == FSB_F32 ? 4 : 8) == 0, "gemm: ldd=%ld not vector-aligned", (long)ldd);
+  FSB_REQUIRE(epilogue >= 0 && epilogue <= 2, "gemm: bad epilogue %d", epilogue);
+  FSB_REQUIRE(aux == nullptr || (aligned16(aux) && ldaux % 8 == 0), "gemm: aux misaligned");
+  FSB_REQUIRE(batch == 1 || (stride_a % 8 == 0 && stride_b % 8 == 0 && stride_d % 8 == 0),
+              "gemm: batch strides must be multiples of 8");
+
+  // Tensor maps: always rank 3 (inner, outer, batch).
+  CUtensorMap tmA, tmB;
+  const bool a_mn = (layout == FSB_GEMM_TN), b_mn = (layout != FSB_GEMM_NT);
+  const int BN = (N > 128) ? 256 : 128;
+  {
+    // A: K-major -> memory [M rows, K inner]; MN-major -> memory [K rows, M inner]
+    uint64_t dims[3] = {uint64_t(a_mn ? M : K), uint64_t(a_mn ? K : M), uint64_t(batch)};
+    uint64_t strides[2] = {uint64_t(lda) * 2, uint64_t(batch > 1 ? stride_a : (a_mn ? K : M) * lda) * 2};
+    uint32_t box[3] = {64, uint32_t(a_mn ? GEMM_BK : GEMM_BM), 1};
+    int rc = make_tmap_bf16(&tmA, A, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {uint64_t(b_mn ? N : K), uint64_t(b_mn ? K : N), uint64_t(batch)};
+    uint64_t strides[2] = {uint64_t(ldb) * 2, uint64_t(batch > 1 ? stride_b : (b_mn ? K : N) * ldb) * 2};
+    uint32_t box[3] = {64, uint32_t(b_mn ? GEMM_BK : BN), 1};
+    int rc = make_tmap_bf16(&tmB, B, 3, dims, strides, box);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  p.D = D; p.aux = aux; p.bias = bias;
+  p.ldd = ldd; p.ldaux = ldaux; p.stride_d = stride_d; p.stride_aux = stride_aux;
+  p.M = int(M); p.N = int(N); p.K = int(K); p.batch = int(batch);
+  p.d_f32 = (d_dtype == FSB_F32); p.bias_f32 = (bias_dtype == FSB_F32);
+  p.epilogue = epilogue; p.accumulate = accumulate;
+  p.tiles_m = int((M + GEMM_BM - 1) / GEMM_BM);
+  p.tiles_n = int((N + BN - 1) / BN);
+
+#define FSB_GEMM_DISPATCH(L)                                                    \
+  case L:                                                                        \
+    return BN == 256 ? launch_gemm<L, 256>(tmA, tmB, p, stream) : launch_gemm<L, 128>(tmA, tmB, p, stream);
+  switch (layout) {
+    FSB_GEMM_DISPATCH(FSB_GEMM_NT)
+    FSB_GEMM_DISPATCH(FSB_GEMM_NN)
+    FSB_GEMM_DISPATCH(FSB_GEMM_TN)
+  }
+#undef FSB_GEMM_DISPATCH
+  return FSB_ERR_INVALID;
+}

@@ -1,0 +1,307 @@
+// fsb200 — RMSNorm / LayerNorm forward + backward (HBM-bound; one pass over each operand).
+//   RMSNorm   : fengshen/models/megatron/layers/norms.py:44-52 (== MT5LayerNorm): y = scale * cast(x * rsqrt(mean(x^2)+eps))
+//   LayerNorm : torch.nn.LayerNorm as re-exported at layers/norms.py:16 (BERT/GPT2/MegatronBERT via transformers)
+// Optional fusions: residual add in forward (x_sum = x + residual is also written out), and "+= dres" in backward
+// (gradient arriving through the residual branch), which removes the two un-fused adds at transformer.py:775-788.
+// Layout: [rows, cols] bf16 row-major, cols % 8 == 0, cols <= 16384. One CTA per row slot, rows strided by gridDim
+// (grid = multiple of the SM count); a row is held in registers between the reduction and the normalisation.
+// Weight gradients: each CTA accumulates a private fp32 partial over its rows -> workspace[grid, cols] -> a second
+// kernel reduces the partials column-wise (deterministic, no atomics).
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace fsb {
+
+constexpr int NORM_THREADS = 256;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// Block-wide sum of up to two values; result broadcast to all threads.
+template <int NT>
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* red /* 2*NT/32 floats */) {
+  constexpr int NW = NT / 32;
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();  // protect red[] reuse
+  if (l == 0) { red[w] = a; red[NW + w] = b; }
+  __syncthreads();
+  float x = (l < NW) ? red[l] : 0.f, y = (l < NW) ? red[NW + l] : 0.f;
+  a = warp_sum(x);
+  b = warp_sum(y);
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// forward.  kLayer = false: RMSNorm (stats[row] = rstd). kLayer = true: LayerNorm (stats[2*row] = mean, [2*row+1] = rstd)
+// ------------------------------------------------------------------------------------------------------------
+template <bool kLayer, int VPT>
+__global__ void __launch_bounds__(NORM_THREADS) norm_fwd_kernel(
+    const uint4* __restrict__ x, const uint4* __restrict__ residual, const uint4* __restrict__ gamma,
+    const uint4* __restrict__ beta, uint4* __restrict__ y, uint4* __restrict__ sum_out, float* __restrict__ stats,
+    int rows, int cols, float eps) {
+  __shared__ float red[2 * NORM_THREADS / 32];
+  const int nvec = cols >> 3;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const size_t base = size_t(row) * nvec;
+    float xv[VPT][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = threadIdx.x + i * NORM_THREADS;
+      if (c < nvec) {
+        uint4 q = x[base + c];
+        unpack8(q, xv[i]);
+        if (residual != nullptr) {
+          float rv[8];
+          unpack8(residual[base + c], rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[i][j] = round_bf16(xv[i][j] + rv[j]);  // the sum lives in bf16 in the reference
+          sum_out[base + c] = pack8(xv[i]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1 += xv[i][j]; s2 += xv[i][j] * xv[i][j]; }
+      }
+    }
+    block_sum2<NORM_THREADS>(s1, s2, red);
+    float mean = 0.f, rstd;
+    if (kLayer) {
+      mean = s1 / cols;
+      // two-pass variance from registers (matches torch's numerically stable form better than E[x^2]-mean^2)
+      float v = 0.f, dummy = 0.f;
+#pragma unroll
+      for (int i = 0; i < VPT; ++i) {
+        const int c = threadIdx.x + i * NORM_THREADS;
+        if (c < nvec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { float d = xv[i][j] - mean; v += d * d; }
+        }
+      }
+      block_sum2<NORM_THREADS>(v, dummy, red);
+      rstd = rsqrtf(v / cols + eps);
+      if (threadIdx.x == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+    } else {
+      rstd = rsqrtf(s2 / cols + eps);
+      if (threadIdx.x == 0) stats[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = threadIdx.x + i * NORM_THREADS;
+      if (c < nvec) {
+        float g[8], o[8];
+        unpack8(gamma[c], g);
+        if (kLayer) {
+          float bt[8];
+          unpack8(beta[c], bt);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = (xv[i][j] - mean) * rstd * g[j] + bt[j];
+        } else {
+          // norms.py:45-52: normalise in fp32, cast to the 16-bit dtype, THEN multiply by scale (16-bit product)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = round_bf16(xv[i][j] * rstd) * g[j];
+        }
+        y[base + c] = pack8(o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward. dx = rstd * (g - xhat * mean(g*xhat) [- mean(g)])  with g = dy * gamma;  partial dgamma/dbeta per CTA.
+// ------------------------------------------------------------------------------------------------------------
+template <bool kLayer, int VPT>
+__global__ void __launch_bounds__(NORM_THREADS) norm_bwd_kernel(
+    const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ gamma,
+    const float* __restrict__ stats, const uint4* __restrict__ dres, uint4* __restrict__ dx,
+    float* __restrict__ partial /* [grid, (kLayer?2:1), cols] */, int rows, int cols) {
+  __shared__ float red[2 * NORM_THREADS / 32];
+  const int nvec = cols >> 3;
+  float dg[VPT][8], db[VPT][8];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; }
+
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const size_t base = size_t(row) * nvec;
+    const float mean = kLayer ? stats[2 * row] : 0.f;
+    const float rstd = kLayer ? stats[2 * row + 1] : stats[row];
+    float xh[VPT][8], g[VPT][8];
+    float s_g = 0.f, s_gx = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = threadIdx.x + i * NORM_THREADS;
+      if (c < nvec) {
+        float xv[8], dyv[8], gm[8];
+        unpack8(x[base + c], xv);
+        unpack8(dy[base + c], dyv);
+        unpack8(gamma[c], gm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xv[j] - mean) * rstd;
+          g[i][j] = dyv[j] * gm[j];
+          s_g += g[i][j];
+          s_gx += g[i][j] * xh[i][j];
+          dg[i][j] += dyv[j] * (kLayer ? xh[i][j] : round_bf16(xh[i][j]));
+          if (kLayer) db[i][j] += dyv[j];
+        }
+      }
+    }
+    block_sum2<NORM_THREADS>(s_g, s_gx, red);
+    const float m_g = kLayer ? s_g / cols : 0.f;
+    const float m_gx = s_gx / cols;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = threadIdx.x + i * NORM_THREADS;
+      if (c < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - m_g - xh[i][j] * m_gx);
+        if (dres != nullptr) {
+          float r[8];
+          unpack8(dres[base + c], r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += r[j];
+        }
+        dx[base + c] = pack8(o);
+      }
+    }
+  }
+  // write this CTA's partial weight gradients
+  float* pg = partial + size_t(blockIdx.x) * (kLayer ? 2 : 1) * cols;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int c = threadIdx.x + i * NORM_THREADS;
+    if (c < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        pg[c * 8 + j] = dg[i][j];
+        if (kLayer) pg[cols + c * 8 + j] = db[i][j];
+      }
+    }
+  }
+}
+
+// Column-wise reduction of partial[nparts, width] (fp32). Columns [0, split) go to out0, [split, width) to out1.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ partial, void* __restrict__ out0,
+                                                     void* __restrict__ out1, int nparts, int width, int split,
+                                                     int out_f32, int accumulate) {
+  __shared__ float sm[8][33];  // 32 columns x 8 row-lanes
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  float s = 0.f;
+  if (col < width)
+    for (int r = rl; r < nparts; r += 8) s += partial[size_t(r) * width + col];
+  sm[rl][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (rl == 0 && col < width) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
+    void* out = col < split ? out0 : out1;
+    const int c = col < split ? col : col - split;
+    if (out_f32) {
+      float* o = reinterpret_cast<float*>(out);
+      o[c] = accumulate ? o[c] + t : t;
+    } else {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+      o[c] = __float2bfloat16(accumulate ? __bfloat162float(o[c]) + t : t);
+    }
+  }
+}
+
+static int norm_grid(int rows) {
+  int g = 4 * num_sms();
+  return rows < g ? rows : g;
+}
+
+template <bool kLayer>
+static int norm_fwd(const void* x, const void* residual, const void* gamma, const void* beta, void* y, void* sum_out,
+                    float* stats, int64_t rows, int64_t cols, float eps, cudaStream_t st) {
+  FSB_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 16384, "norm_fwd: bad shape rows=%ld cols=%ld", (long)rows,
+              (long)cols);
+  FSB_REQUIRE(x && gamma && y && stats && (!kLayer || beta), "norm_fwd: null pointer");
+  FSB_REQUIRE(residual == nullptr || sum_out != nullptr, "norm_fwd: residual given without sum_out");
+  FSB_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(residual) && aligned16(sum_out) &&
+                  aligned16(beta),
+              "norm_fwd: pointers must be 16-byte aligned");
+  const int nvec = int(cols / 8);
+  const int vpt = (nvec + NORM_THREADS - 1) / NORM_THREADS;
+  const int grid = norm_grid(int(rows));
+#define L(V)                                                                                                        \
+  norm_fwd_kernel<kLayer, V><<<grid, NORM_THREADS, 0, st>>>((const uint4*)x, (const uint4*)residual,               \
+                                                            (const uint4*)gamma, (const uint4*)beta, (uint4*)y,    \
+                                                            (uint4*)sum_out, stats, int(rows), int(cols), eps)
+  switch (vpt) {
+    case 1: L(1); break; case 2: L(2); break; case 3: L(3); break; case 4: L(4); break;
+    case 5: L(5); break; case 6: L(6); break; case 7: L(7); break; default: L(8); break;
+  }
+#undef L
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+
+template <bool kLayer>
+static int norm_bwd(const void* dy, const void* x, const void* gamma, const float* stats, const void* dres, void* dx,
+                    void* dgamma, void* dbeta, int wgrad_dtype, int accumulate, void* workspace, size_t ws_bytes,
+                    int64_t rows, int64_t cols, cudaStream_t st) {
+  FSB_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && cols <= 16384, "norm_bwd: bad shape rows=%ld cols=%ld", (long)rows,
+              (long)cols);
+  FSB_REQUIRE(dy && x && gamma && stats && dx && dgamma && workspace && (!kLayer || dbeta), "norm_bwd: null pointer");
+  FSB_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(gamma) && aligned16(dres) && aligned16(dx),
+              "norm_bwd: pointers must be 16-byte aligned");
+  const int grid = norm_grid(int(rows));
+  const int width = int(cols) * (kLayer ? 2 : 1);
+  const size_t need = size_t(grid) * width * sizeof(float);
+  FSB_REQUIRE(ws_bytes >= need, "norm_bwd: workspace %zu < %zu bytes", ws_bytes, need);
+  const int nvec = int(cols / 8);
+  const int vpt = (nvec + NORM_THREADS - 1) / NORM_THREADS;
+#define L(V)                                                                                                      \
+  norm_bwd_kernel<kLayer, V><<<grid, NORM_THREADS, 0, st>>>((const uint4*)dy, (const uint4*)x, (const uint4*)gamma, \
+                                                            stats, (const uint4*)dres, (uint4*)dx,                \
+                                                            (float*)workspace, int(rows), int(cols))
+  switch (vpt) {
+    case 1: L(1); break; case 2: L(2); break; case 3: L(3); break; case 4: L(4); break;
+    case 5: L(5); break; case 6: L(6); break; case 7: L(7); break; default: L(8); break;
+  }
+#undef L
+  FSB_CUDA_LAUNCH_CHECK();
+  colsum_kernel<<<(width + 31) / 32, 256, 0, st>>>((const float*)workspace, dgamma, dbeta, grid, width, int(cols),
+                                                   wgrad_dtype == FSB_F32, accumulate);
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+
+}  // namespace fsb
+
+using namespace fsb;
+
+extern "C" size_t fsb_norm_bwd_workspace_bytes(int64_t rows, int64_t cols, int is_layernorm) {
+  const int grid = norm_grid(int(rows));
+  return size_t(grid) * size_t(cols) * (is_layernorm ? 2 : 1) * sizeof(float);
+}
+extern "C" int fsb_rmsnorm_fwd(const void* x, const void* residual, const void* scale, void* y, void* sum_out,
+                               float* rstd, int64_t rows, int64_t cols, float eps, fsb_stream_t st) {
+  return norm_fwd<false>(x, residual, scale, nullptr, y, sum_out, rstd, rows, cols, eps, (cudaStream_t)st);
+}
+extern "C" int fsb_rmsnorm_bwd(const void* dy, const void* x, const void* scale, const float* rstd, const void* dres,
+                               void* dx, void* dscale, int wgrad_dtype, int accumulate, void* workspace,
+                               size_t workspace_bytes, int64_t rows, int64_t cols, fsb_stream_t st) {
+  return norm_bwd<false>(dy, x, scale, rstd, dres, dx, dscale, nullptr, wgrad_dtype, accumulate, workspace,
+                         workspace_bytes, rows, cols, (cudaStream_t)st);
+}
+extern "C" int fsb_layernorm_fwd(const void* x, const void* residual, const void* gamma, const void* beta, void* y,
+                                 void* sum_out, float* mean_rstd, int64_t rows, int64_t cols, float eps,
+                                 fsb_stream_t st) {
+  return norm_fwd<true>(x, residual, gamma, beta, y, sum_out, mean_rstd, rows, cols, eps, (cudaStream_t)st);
+}
+extern "C" int fsb_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean_rstd,
+                                 const void* dres, void* dx, void* dgamma, void* dbeta, int wgrad_dtype,
+                                 int accumulate, void* workspace, size_t workspace_bytes, int64_t rows, int64_t cols,
+                                 fsb_stream_t st) {
+  return norm_bwd<true>(dy, x, gamma, mean_rstd, dres, dx, dgamma, dbeta, wgrad_dtype, accumulate, workspace,
+                        workspace_bytes, rows, cols, (cudaStream_t)st);
+}

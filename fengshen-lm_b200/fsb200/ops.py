@@ -1,0 +1,220 @@
+"""Tensor-level wrappers over the C ABI: torch is used only for device memory and the current stream.
+
+Each function validates what the C side cannot know (dtype, device, contiguity) and forwards raw pointers.
+No function here has a PyTorch fallback path.
+"""
+import torch
+
+from . import lib as L
+
+_bf16 = torch.bfloat16
+_ws_cache = {}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise RuntimeError(f"fsb200: {name} must be a CUDA tensor (the hot path has no CPU fallback)")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"fsb200: {name} must be {dtype}, got {t.dtype}")
+
+
+def _rows2d(t, name):
+    """View as [rows, cols] with unit inner stride; returns (rows, cols, ld)."""
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise RuntimeError(f"fsb200: {name} must be 2-D with unit inner stride, got shape {tuple(t.shape)} "
+                           f"strides {t.stride()}")
+    return t.shape[0], t.shape[1], t.stride(0)
+
+
+def workspace(nbytes, device, tag="default"):
+    """Grow-only scratch buffer per (device, tag); caller-owned from the library's point of view."""
+    key = (device, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------------------------------------------ GEMM
+def gemm(layout, a, b, out=None, out_dtype=_bf16, bias=None, epilogue=L.EPI_NONE, accumulate=False, aux=None):
+    """layout NT: a[M,K] b[N,K]; NN: a[M,K] b[K,N]; TN: a[K,M] b[K,N]. Returns out[M,N]."""
+    _chk(a, _bf16, "a"); _chk(b, _bf16, "b")
+    ar, ac, lda = _rows2d(a, "a")
+    br, bc, ldb = _rows2d(b, "b")
+    if layout == L.GEMM_NT:
+        M, K, N = ar, ac, br
+        if bc != K: raise RuntimeError(f"fsb200 gemm NT: K mismatch {ac} vs {bc}")
+    elif layout == L.GEMM_NN:
+        M, K, N = ar, ac, bc
+        if br != K: raise RuntimeError(f"fsb200 gemm NN: K mismatch {ac} vs {br}")
+    else:
+        K, M, N = ar, ac, bc
+        if br != K: raise RuntimeError(f"fsb200 gemm TN: K mismatch {ar} vs {br}")
+    if out is None:
+        if accumulate: raise RuntimeError("fsb200 gemm: accumulate needs an existing `out`")
+        out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    _chk(out, None, "out")
+    if out.dtype not in (_bf16, torch.float32): raise RuntimeError("fsb200 gemm: out must be bf16 or fp32")
+    orr, occ, ldd = _rows2d(out, "out")
+    if (orr, occ) != (M, N): raise RuntimeError(f"fsb200 gemm: out shape {tuple(out.shape)} != ({M},{N})")
+    bias_dt = L.BF16
+    if bias is not None:
+        _chk(bias, None, "bias")
+        if bias.numel() != N or not bias.is_contiguous(): raise RuntimeError("fsb200 gemm: bias must be contiguous [N]")
+        bias_dt = L.F32 if bias.dtype == torch.float32 else L.BF16
+    ldaux = 0
+    if aux is not None:
+        _chk(aux, _bf16, "aux")
+        _, _, ldaux = _rows2d(aux, "aux")
+    L.call("fsb_gemm_bf16", layout, M, N, K, _p(a), lda, _p(b), ldb, _p(out), ldd,
+           L.F32 if out.dtype == torch.float32 else L.BF16, _p(bias), bias_dt, epilogue, int(bool(accumulate)),
+           _p(aux), ldaux, 1, 0, 0, 0, 0, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------ norms
+def rmsnorm_fwd(x, scale, eps, residual=None):
+    """x [rows, cols] bf16. Returns (y, rstd, x_sum) where x_sum = x + residual (or x itself when residual is None)."""
+    _chk(x, _bf16, "x"); _chk(scale, _bf16, "scale")
+    rows, cols = x.shape
+    y = torch.empty_like(x)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    xs = torch.empty_like(x) if residual is not None else None
+    L.call("fsb_rmsnorm_fwd", _p(x), _p(residual), _p(scale), _p(y), _p(xs), _p(rstd), rows, cols, float(eps), _stream())
+    return y, rstd, (xs if residual is not None else x)
+
+
+def rmsnorm_bwd(dy, x, scale, rstd, dscale_out, accumulate=False, dres=None):
+    rows, cols = x.shape
+    dx = torch.empty_like(x)
+    nbytes = L.load().fsb_norm_bwd_workspace_bytes(rows, cols, 0)
+    ws = workspace(nbytes, x.device, "norm")
+    L.call("fsb_rmsnorm_bwd", _p(dy), _p(x), _p(scale), _p(rstd), _p(dres), _p(dx), _p(dscale_out),
+           L.F32 if dscale_out.dtype == torch.float32 else L.BF16, int(bool(accumulate)), _p(ws), ws.numel(), rows, cols,
+           _stream())
+    return dx
+
+
+def layernorm_fwd(x, gamma, beta, eps, residual=None):
+    _chk(x, _bf16, "x"); _chk(gamma, _bf16, "gamma"); _chk(beta, _bf16, "beta")
+    rows, cols = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty(rows, 2, dtype=torch.float32, device=x.device)
+    xs = torch.empty_like(x) if residual is not None else None
+    L.call("fsb_layernorm_fwd", _p(x), _p(residual), _p(gamma), _p(beta), _p(y), _p(xs), _p(stats), rows, cols,
+           float(eps), _stream())
+    return y, stats, (xs if residual is not None else x)
+
+
+def layernorm_bwd(dy, x, gamma, stats, dgamma_out, dbeta_out, accumulate=False, dres=None):
+    rows, cols = x.shape
+    dx = torch.empty_like(x)
+    nbytes = L.load().fsb_norm_bwd_workspace_bytes(rows, cols, 1)
+    ws = workspace(nbytes, x.device, "norm")
+    L.call("fsb_layernorm_bwd", _p(dy), _p(x), _p(gamma), _p(stats), _p(dres), _p(dx), _p(dgamma_out), _p(dbeta_out),
+           L.F32 if dgamma_out.dtype == torch.float32 else L.BF16, int(bool(accumulate)), _p(ws), ws.numel(), rows, cols,
+           _stream())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------------ pointwise
+def rope_inplace(x, cos, sin, positions, nheads, head_dim, row_stride, head_stride, backward=False, offset=0):
+    """Rotate `nheads` heads per row in place. x is the flat packed buffer; `offset` (elements) selects q or k."""
+    _chk(x, _bf16, "x")
+    rows = positions.numel()
+    L.call("fsb_rope_inplace", x.data_ptr() + 2 * offset, _p(cos), _p(sin), _p(positions), rows, nheads, head_dim,
+           row_stride, head_stride, cos.shape[0], int(bool(backward)), _stream())
+
+
+def glu_fwd(act, gate, up):
+    rows, cols, ldg = _rows2d(gate, "gate")
+    _, _, ldu = _rows2d(up, "up")
+    out = torch.empty((rows, cols), dtype=_bf16, device=gate.device)
+    L.call("fsb_glu_fwd", act, _p(gate), _p(up), _p(out), rows, cols, ldg, ldu, cols, _stream())
+    return out
+
+
+def glu_bwd(act, dout, gate, up, dgate, dup):
+    rows, cols, ldg = _rows2d(gate, "gate")
+    _, _, ldu = _rows2d(up, "up")
+    _, _, ldo = _rows2d(dout, "dout")
+    _, _, ldg2 = _rows2d(dgate, "dgate")
+    _, _, ldu2 = _rows2d(dup, "dup")
+    L.call("fsb_glu_bwd", act, _p(dout), _p(gate), _p(up), _p(dgate), _p(dup), rows, cols, ldo, ldg, ldu, ldg2, ldu2,
+           _stream())
+
+
+def act_fwd(act, x):
+    y = torch.empty_like(x)
+    L.call("fsb_act_fwd", act, _p(x), _p(y), x.numel(), _stream())
+    return y
+
+
+def act_bwd(act, dy, x):
+    dx = torch.empty_like(x)
+    L.call("fsb_act_bwd", act, _p(dy), _p(x), _p(dx), x.numel(), _stream())
+    return dx
+
+
+def add(a, b, out=None):
+    if out is None: out = torch.empty_like(a)
+    L.call("fsb_add", _p(a), _p(b), _p(out), a.numel(), _stream())
+    return out
+
+
+def embedding_fwd(ids, W, pos=None, P=None, token_type=None, T=None, seq_len=1):
+    rows = ids.numel()
+    cols = W.shape[1]
+    out = torch.empty((rows, cols), dtype=_bf16, device=W.device)
+    L.call("fsb_embedding_fwd", _p(ids), _p(pos), _p(token_type), _p(W), _p(P), _p(T), _p(out), rows, cols, seq_len,
+           _stream())
+    return out
+
+
+def embedding_bwd(ids, dout, dW, idx_mod=0):
+    rows, cols = dout.shape
+    L.call("fsb_embedding_bwd", _p(ids), _p(dout), _p(dW), rows, cols, idx_mod, _stream())
+
+
+# ------------------------------------------------------------------------------------------------------ loss / optim
+def softmax_xent(logits, labels, seq_len, shift=1, ignore_index=-100, grad_scale=1.0, dlogits="inplace"):
+    """logits [rows, V] bf16 (rows = b*seq_len), labels int64 [rows]. Returns (loss scalar tensor, dlogits, n_valid)."""
+    _chk(logits, _bf16, "logits")
+    rows, V, ld = _rows2d(logits, "logits")
+    dev = logits.device
+    row_loss = torch.empty(rows, dtype=torch.float32, device=dev)
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    n_valid = torch.empty((), dtype=torch.int32, device=dev)
+    if isinstance(dlogits, str):
+        dl = logits if dlogits == "inplace" else None
+    else:
+        dl = dlogits
+    L.call("fsb_softmax_xent_fwd_bwd", _p(logits), _p(labels), _p(dl), _p(row_loss), _p(loss), _p(n_valid), rows, V, ld,
+           seq_len, shift, ignore_index, float(grad_scale), _stream())
+    return loss, dl, n_valid
+
+
+def adamw_flat(master, m, v, grad, param16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None):
+    L.call("fsb_adamw_flat", _p(master), _p(m), _p(v), _p(grad), L.F32 if grad.dtype == torch.float32 else L.BF16,
+           _p(param16), master.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+           _p(grad_scale), _stream())
+
+
+def sumsq(x, out, accumulate=False):
+    nbytes = L.load().fsb_sumsq_workspace_bytes()
+    ws = workspace(nbytes, x.device, "sumsq")
+    L.call("fsb_sumsq", _p(x), L.F32 if x.dtype == torch.float32 else L.BF16, x.numel(), _p(out), int(bool(accumulate)),
+           _p(ws), ws.numel(), _stream())
+
+
+def clip_coef(sumsq_t, max_norm, coef_out, norm_out=None):
+    L.call("fsb_clip_coef", _p(sumsq_t), float(max_norm), _p(coef_out), _p(norm_out), _stream())
