@@ -218,3 +218,33 @@ def sumsq(x, out, accumulate=False):
 
 def clip_coef(sumsq_t, max_norm, coef_out, norm_out=None):
     L.call("fsb_clip_coef", _p(sumsq_t), float(max_norm), _p(coef_out), _p(norm_out), _stream())
+
+
+# ------------------------------------------------------------------------------------------------------ attention
+def _bshd(t, name):
+    """[batch, seq, heads, dim] view with unit inner stride and batch stride == seq * row stride."""
+    if t.dim() != 4 or t.stride(3) != 1:
+        raise RuntimeError(f"fsb200: {name} must be [batch, seq, heads, dim] with unit inner stride")
+    B, S, H, D = t.shape
+    if B > 1 and t.stride(0) != S * t.stride(1):
+        raise RuntimeError(f"fsb200: {name} batch stride {t.stride(0)} != seq*row_stride {S * t.stride(1)}")
+    return B, S, H, D, t.stride(1), t.stride(2)
+
+
+def sdpa_fwd(q, k, v, scale, causal, kv_mask=None, out=None):
+    """q,k,v: strided [B,S,H,D] bf16 views (e.g. slices of the packed QKV projection). Returns (out [B,Sq,H,D], lse)."""
+    _chk(q, _bf16, "q"); _chk(k, _bf16, "k"); _chk(v, _bf16, "v")
+    B, Sq, H, D, q_rs, q_hs = _bshd(q, "q")
+    _, Skv, _, _, k_rs, k_hs = _bshd(k, "k")
+    _, _, _, _, v_rs, v_hs = _bshd(v, "v")
+    if out is None:
+        out = torch.empty((B, Sq, H, D), dtype=_bf16, device=q.device)
+    _, _, _, _, o_rs, o_hs = _bshd(out, "out")
+    lse = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
+    if kv_mask is not None:
+        _chk(kv_mask, torch.uint8, "kv_mask")
+        if tuple(kv_mask.shape) != (B, Skv) or not kv_mask.is_contiguous():
+            raise RuntimeError("fsb200: kv_mask must be contiguous uint8 [batch, seq_kv]")
+    L.call("fsb_sdpa_fwd", _p(q), _p(k), _p(v), _p(out), _p(lse), B, Sq, Skv, H, D, q_rs, k_rs, v_rs, o_rs, q_hs, k_hs,
+           v_hs, o_hs, float(scale), int(bool(causal)), _p(kv_mask), _stream())
+    return out, lse

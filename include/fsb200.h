@@ -72,6 +72,21 @@ int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K,
                   int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_d, int64_t stride_aux,
                   fsb_stream_t stream);
 
+/* ---- fused scaled-dot-product attention (tcgen05, flash-style online softmax) ------------------------------
+ * Replaces ParallelSelfAttention.flash_attention (fengshen/models/megatron/layers/transformer.py:410-456; 3P
+ * flash_attn_cuda.fwd/bwd, layers/flash_attention.py:31-47,81-101) and the legacy baddbmm -> FusedScaleMaskSoftmax ->
+ * bmm path (transformer.py:307-408). q/k/v are read in place from the packed QKV projection output:
+ *   element (b, s, head, d) of X lives at X + ((b*seq + s)*x_row_stride + head*x_head_stride + d)  (elements).
+ * o: same addressing with o_*_stride. lse: fp32 [batch, nheads, seq_q], log2 domain (internal, consumed by bwd).
+ * kv_mask: optional uint8 [batch, seq_kv], 1 = attend (HF additive padding mask), NULL = none.
+ * causal=1 masks key > query (requires seq_q == seq_kv). head_dim in {64, 128}.
+ */
+int fsb_sdpa_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                 int64_t batch, int64_t seq_q, int64_t seq_kv, int nheads, int head_dim,
+                 int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride,
+                 int64_t q_head_stride, int64_t k_head_stride, int64_t v_head_stride, int64_t o_head_stride,
+                 float scale, int causal, const uint8_t* kv_mask, fsb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
