@@ -1,0 +1,609 @@
+// fsb200 — fused attention backward on tcgen05 / TMEM (replaces 3P flash_attn_cuda.bwd called from
+// fengshen/models/megatron/layers/flash_attention.py:81-101 and the autograd of the baddbmm/softmax/bmm path,
+// transformer.py:307-408; softmax backward formula dx = y*(dy - sum(dy*y)) as in scaled_masked_softmax.h:240-335).
+//
+// Three launches, all deterministic (no atomics):
+//   1. delta[b,h,q] = sum_d dO*O                                   (HBM-bound preprocess)
+//   2. dQ kernel : CTA = (b, head, 128 queries), loops over 64-key steps:
+//        S = Q K^T, dP = dO V^T  (TMEM, double-buffered)  ->  threads (1 per query row): P = exp2(S*c - lse),
+//        dS = P*(dP - delta) -> bf16 smem (K-major, 128B swizzle)  ->  dQ += dS K  (TMEM accumulator, K as MN-major B)
+//   3. dKV kernel: CTA = (b, head, 128 keys), loops over 64-query steps with the TRANSPOSED products so that
+//        TMEM lane == key row:  S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T (bf16 smem) -> dV += P^T dO, dK += dS^T Q
+//        (dO / Q tiles reused as MN-major B operands; nothing is transposed in memory).
+// S and dP are recomputed in both kernels (7 GEMMs instead of 5) — the price of determinism without a dQ reduction.
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace fsb {
+
+int make_attn_tmap(CUtensorMap* tm, const void* base, int64_t row_stride, int64_t width, int64_t seq, int64_t batch,
+                   int box_rows);
+
+constexpr int AB_THREADS = 192;  // warps 0-3: math warpgroup; warp 4: TMA; warp 5: MMA + TMEM owner
+constexpr int AB_BM = 128;       // rows owned by the CTA (queries for dQ, keys for dKV) == TMEM lanes
+constexpr int AB_BN = 64;        // streamed tile (keys for dQ, queries for dKV)
+
+struct AttBwdParams {
+  const float* lse;     // [B,H,Sq] log2 domain
+  const float* delta;   // [B,H,Sq]
+  const uint8_t* kv_mask;
+  __nv_bfloat16 *dq, *dk, *dv;
+  int64_t dq_row_stride, dk_row_stride, dv_row_stride, dq_head_stride, dk_head_stride, dv_head_stride;
+  int q_head_stride, k_head_stride, v_head_stride, do_head_stride;
+  int seq_q, seq_kv, nheads, batch, causal;
+  float scale, scale_log2;
+};
+
+// ------------------------------------------------------------------------------------------------ delta preprocess
+template <int D>
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
+                                                         const __nv_bfloat16* __restrict__ dout, float* __restrict__ delta,
+                                                         int64_t o_row_stride, int64_t o_head_stride,
+                                                         int64_t do_row_stride, int64_t do_head_stride, int batch, int seq,
+                                                         int nheads) {
+  // one group of D/8 threads per (b, s, h)
+  constexpr int G = D / 8;
+  const int64_t gid = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) / G;
+  const int gl = threadIdx.x % G;
+  const int64_t total = int64_t(batch) * seq * nheads;
+  float s = 0.f;
+  int64_t bs = 0; int h = 0;
+  if (gid < total) {
+    h = int(gid % nheads);
+    bs = gid / nheads;
+    float a[8], b[8];
+    unpack8(*reinterpret_cast<const uint4*>(o + bs * o_row_stride + h * o_head_stride + gl * 8), a);
+    unpack8(*reinterpret_cast<const uint4*>(dout + bs * do_row_stride + h * do_head_stride + gl * 8), b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j] * b[j];
+  }
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (gid < total && gl == 0) {
+    const int64_t b = bs / seq, sq = bs % seq;
+    delta[(b * nheads + h) * seq + sq] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ shared layout
+template <int D>
+struct AttBwdSmem {
+  static constexpr int BIG_BYTES = AB_BM * D * 2;    // a resident 128-row tile
+  static constexpr int SML_BYTES = AB_BN * D * 2;    // a streamed 64-row tile
+  static constexpr int T_BYTES = AB_BM * AB_BN * 2;  // bf16 [128 x 64] P / dS tile
+  static constexpr int STAGES = 2;
+  static constexpr int OFF_BIG0 = 0;                       // dQ: Q     | dKV: K
+  static constexpr int OFF_BIG1 = OFF_BIG0 + BIG_BYTES;    // dQ: dO    | dKV: V
+  static constexpr int OFF_SML0 = OFF_BIG1 + BIG_BYTES;    // dQ: K_j   | dKV: Q_i   (STAGES)
+  static constexpr int OFF_SML1 = OFF_SML0 + STAGES * SML_BYTES;  // dQ: V_j | dKV: dO_i
+  static constexpr int OFF_T0 = OFF_SML1 + STAGES * SML_BYTES;    // dQ: dS[2] | dKV: P^T[2]
+  static constexpr int OFF_T1 = OFF_T0 + 2 * T_BYTES;             //           | dKV: dS^T[2]
+  static constexpr int OFF_STATS = OFF_T1 + 2 * T_BYTES;          // float [2][2][64] (dKV only)
+  static constexpr int OFF_BAR = OFF_STATS + 2 * 2 * 64 * 4;
+  static constexpr int NBAR = 1 + 2 * STAGES + 2 + 2 + 1;  // big_full, sml_full[S], sml_empty[S], s_full[2], t_ready[2], done
+  static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
+};
+
+// ================================================================================================ dQ kernel
+template <int D>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const AttBwdParams p) {
+  using S = AttBwdSmem<D>;
+  constexpr int STAGES = S::STAGES;
+  constexpr int TMEM_COLS = 512;
+  constexpr int TM_S = 0;     // S[buf] at buf*128, dP[buf] at buf*128 + 64
+  constexpr int TM_DQ = 256;  // D columns
+  constexpr uint32_t IDESC_S = make_idesc_bf16(AB_BM, AB_BN, 0, 0);
+  constexpr uint32_t IDESC_DQ = make_idesc_bf16(AB_BM, D, 0, 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* big_full = bars;
+  uint64_t* sml_full = big_full + 1;
+  uint64_t* sml_empty = sml_full + STAGES;
+  uint64_t* s_full = sml_empty + STAGES;
+  uint64_t* t_ready = s_full + 2;
+  uint64_t* done = t_ready + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = gridDim.x - 1 - blockIdx.x;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int q0 = tile * AB_BM;
+  const int n_all = (p.seq_kv + AB_BN - 1) / AB_BN;
+  const int n_steps = p.causal ? min(n_all, (min(q0 + AB_BM, p.seq_q) + AB_BN - 1) / AB_BN) : n_all;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(big_full, 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&sml_full[i], 1); mbar_init(&sml_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&t_ready[i], AB_BM); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const int qc = head * p.q_head_stride, dc = head * p.do_head_stride;
+      const int kc = head * p.k_head_stride, vc = head * p.v_head_stride;
+      mbar_expect_tx(big_full, 2 * S::BIG_BYTES);
+#pragma unroll
+      for (int h = 0; h < D / 64; ++h) {
+        tma_load_3d(smem + S::OFF_BIG0 + h * (AB_BM * 128), &tmQ, big_full, qc + h * 64, q0, b);
+        tma_load_3d(smem + S::OFF_BIG1 + h * (AB_BM * 128), &tmdO, big_full, dc + h * 64, q0, b);
+      }
+      int st = 0; uint32_t ph = 0;
+      for (int j = 0; j < n_steps; ++j) {
+        mbar_wait(&sml_empty[st], ph ^ 1);
+        mbar_expect_tx(&sml_full[st], 2 * S::SML_BYTES);
+#pragma unroll
+        for (int h = 0; h < D / 64; ++h) {
+          tma_load_3d(smem + S::OFF_SML0 + st * S::SML_BYTES + h * (AB_BN * 128), &tmK, &sml_full[st], kc + h * 64,
+                      j * AB_BN, b);
+          tma_load_3d(smem + S::OFF_SML1 + st * S::SML_BYTES + h * (AB_BN * 128), &tmV, &sml_full[st], vc + h * 64,
+                      j * AB_BN, b);
+        }
+        if (++st == STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      auto issue_s_dp = [&](int buf, int st) {
+        const uint32_t sq = smem_u32(smem + S::OFF_BIG0), sdo = smem_u32(smem + S::OFF_BIG1);
+        const uint32_t sk = smem_u32(smem + S::OFF_SML0 + st * S::SML_BYTES);
+        const uint32_t sv = smem_u32(smem + S::OFF_SML1 + st * S::SML_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t oa = (kk / 4) * (AB_BM * 128) + (kk % 4) * 32, ob = (kk / 4) * (AB_BN * 128) + (kk % 4) * 32;
+          umma_bf16(tmem_base + TM_S + buf * 128, make_smem_desc_sw128(sq + oa, 0, 1024),
+                    make_smem_desc_sw128(sk + ob, 0, 1024), IDESC_S, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t oa = (kk / 4) * (AB_BM * 128) + (kk % 4) * 32, ob = (kk / 4) * (AB_BN * 128) + (kk % 4) * 32;
+          umma_bf16(tmem_base + TM_S + buf * 128 + 64, make_smem_desc_sw128(sdo + oa, 0, 1024),
+                    make_smem_desc_sw128(sv + ob, 0, 1024), IDESC_S, kk != 0);
+        }
+      };
+      mbar_wait(big_full, 0);
+      if (n_steps > 0) {
+        mbar_wait(&sml_full[0], 0);
+        tc_fence_after();
+        issue_s_dp(0, 0);
+        umma_commit(&s_full[0]);
+      }
+      int st = 0; uint32_t ph = 0;
+      for (int j = 0; j < n_steps; ++j) {
+        int st1 = st + 1; uint32_t ph1 = ph;
+        if (st1 == STAGES) { st1 = 0; ph1 ^= 1; }
+        if (j + 1 < n_steps) {
+          mbar_wait(&sml_full[st1], ph1);
+          tc_fence_after();
+          issue_s_dp((j + 1) & 1, st1);
+          umma_commit(&s_full[(j + 1) & 1]);
+        }
+        mbar_wait(&t_ready[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t sds = smem_u32(smem + S::OFF_T0 + (j & 1) * S::T_BYTES);
+        const uint32_t sk = smem_u32(smem + S::OFF_SML0 + st * S::SML_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < AB_BN / 16; ++kk)
+          umma_bf16(tmem_base + TM_DQ, make_smem_desc_sw128(sds + kk * 32, 0, 1024),
+                    make_smem_desc_sw128(sk + kk * 2048, AB_BN * 128, 1024), IDESC_DQ, (j | kk) != 0);
+        umma_commit(&sml_empty[st]);
+        st = st1; ph = ph1;
+      }
+      umma_commit(done);
+    }
+  } else {
+    // ---- math warpgroup: one thread per query row
+    const int quad = warp & 3;
+    const int r_in = quad * 32 + lane;
+    const int q_row = q0 + r_in;
+    const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16);
+    const bool row_ok = q_row < p.seq_q;
+    const int64_t stat_idx = (int64_t(b) * p.nheads + head) * p.seq_q + q_row;
+    const float lse = row_ok ? p.lse[stat_idx] : INFINITY;
+    const float delta = row_ok ? p.delta[stat_idx] : 0.f;
+    const uint8_t* mrow = p.kv_mask ? p.kv_mask + int64_t(b) * p.seq_kv : nullptr;
+    const int sw = r_in & 7;
+    for (int j = 0; j < n_steps; ++j) {
+      const int buf = j & 1;
+      mbar_wait(&s_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t s0[32], s1[32];
+      tmem_ld32(t_lane + TM_S + buf * 128, s0);
+      tmem_ld32(t_lane + TM_S + buf * 128 + 32, s1);
+      tmem_ld_wait();
+      const int kv0 = j * AB_BN;
+      const bool need_mask = (p.causal && kv0 + AB_BN - 1 > q0) || (kv0 + AB_BN > p.seq_kv) || mrow;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        float pv = exp2f(__uint_as_float(c < 32 ? s0[c & 31] : s1[c & 31]) * p.scale_log2 - lse);
+        if (need_mask) {
+          const int col = kv0 + c;
+          bool keep = col < p.seq_kv && !(p.causal && col > q_row);
+          if (keep && mrow) keep = mrow[col] != 0;
+          pv = keep ? pv : 0.f;
+        }
+        if (c < 32) s0[c & 31] = __float_as_uint(pv); else s1[c & 31] = __float_as_uint(pv);
+      }
+      uint8_t* sds = smem + S::OFF_T0 + buf * S::T_BYTES + r_in * 128;
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {
+        uint32_t d[32];
+        tmem_ld32(t_lane + TM_S + buf * 128 + 64 + hc * 32, d);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float p0 = __uint_as_float(hc == 0 ? s0[c] : s1[c]), p1 = __uint_as_float(hc == 0 ? s0[c + 1] : s1[c + 1]);
+          pk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(d[c]) - delta), p1 * (__uint_as_float(d[c + 1]) - delta));
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+          *reinterpret_cast<uint4*>(sds + (((hc * 4 + ch) ^ sw) << 4)) =
+              make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&t_ready[buf]);
+    }
+    // ---- epilogue
+    mbar_wait(done, 0);
+    tc_fence_after();
+    if (n_steps > 0) {
+      __nv_bfloat16* dqp = p.dq + (int64_t(b) * p.seq_q + q_row) * p.dq_row_stride + int64_t(head) * p.dq_head_stride;
+#pragma unroll
+      for (int ch = 0; ch < D / 32; ++ch) {
+        uint32_t t[32];
+        tmem_ld32(t_lane + TM_DQ + ch * 32, t);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(t[c + e]) * p.scale;
+            *reinterpret_cast<uint4*>(dqp + ch * 32 + c) = pack8(f);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ================================================================================================ dK / dV kernel
+template <int D>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                    const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                    const AttBwdParams p) {
+  using S = AttBwdSmem<D>;
+  constexpr int STAGES = S::STAGES;
+  constexpr int TMEM_COLS = 512;
+  constexpr int TM_S = 0;             // S^T[buf] at buf*128, dP^T[buf] at buf*128 + 64
+  constexpr int TM_DV = 256;          // D columns
+  constexpr int TM_DK = 256 + D;      // D columns (D <= 128)
+  constexpr uint32_t IDESC_S = make_idesc_bf16(AB_BM, AB_BN, 0, 0);
+  constexpr uint32_t IDESC_DKV = make_idesc_bf16(AB_BM, D, 0, 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* big_full = bars;
+  uint64_t* sml_full = big_full + 1;
+  uint64_t* sml_empty = sml_full + STAGES;
+  uint64_t* s_full = sml_empty + STAGES;
+  uint64_t* t_ready = s_full + 2;
+  uint64_t* done = t_ready + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done + 1);
+  float* stats = reinterpret_cast<float*>(smem + S::OFF_STATS);  // [buf][0: lse, 1: delta][64]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;  // early key tiles see the most queries under a causal mask: they come first already
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int kv0 = tile * AB_BM;
+  const int n_q = (p.seq_q + AB_BN - 1) / AB_BN;
+  const int i_start = p.causal ? min(n_q, kv0 / AB_BN) : 0;
+  const int n_steps = n_q - i_start;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+    mbar_init(big_full, 1);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&sml_full[i], 1); mbar_init(&sml_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&t_ready[i], AB_BM); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const int qc = head * p.q_head_stride, dc = head * p.do_head_stride;
+      const int kc = head * p.k_head_stride, vc = head * p.v_head_stride;
+      mbar_expect_tx(big_full, 2 * S::BIG_BYTES);
+#pragma unroll
+      for (int h = 0; h < D / 64; ++h) {
+        tma_load_3d(smem + S::OFF_BIG0 + h * (AB_BM * 128), &tmK, big_full, kc + h * 64, kv0, b);
+        tma_load_3d(smem + S::OFF_BIG1 + h * (AB_BM * 128), &tmV, big_full, vc + h * 64, kv0, b);
+      }
+      int st = 0; uint32_t ph = 0;
+      for (int i = 0; i < n_steps; ++i) {
+        mbar_wait(&sml_empty[st], ph ^ 1);
+        mbar_expect_tx(&sml_full[st], 2 * S::SML_BYTES);
+#pragma unroll
+        for (int h = 0; h < D / 64; ++h) {
+          tma_load_3d(smem + S::OFF_SML0 + st * S::SML_BYTES + h * (AB_BN * 128), &tmQ, &sml_full[st], qc + h * 64,
+                      (i_start + i) * AB_BN, b);
+          tma_load_3d(smem + S::OFF_SML1 + st * S::SML_BYTES + h * (AB_BN * 128), &tmdO, &sml_full[st], dc + h * 64,
+                      (i_start + i) * AB_BN, b);
+        }
+        if (++st == STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      auto issue_st_dpt = [&](int buf, int st) {
+        const uint32_t sk = smem_u32(smem + S::OFF_BIG0), sv = smem_u32(smem + S::OFF_BIG1);
+        const uint32_t sq = smem_u32(smem + S::OFF_SML0 + st * S::SML_BYTES);
+        const uint32_t sdo = smem_u32(smem + S::OFF_SML1 + st * S::SML_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t oa = (kk / 4) * (AB_BM * 128) + (kk % 4) * 32, ob = (kk / 4) * (AB_BN * 128) + (kk % 4) * 32;
+          umma_bf16(tmem_base + TM_S + buf * 128, make_smem_desc_sw128(sk + oa, 0, 1024),
+                    make_smem_desc_sw128(sq + ob, 0, 1024), IDESC_S, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk) {
+          const uint32_t oa = (kk / 4) * (AB_BM * 128) + (kk % 4) * 32, ob = (kk / 4) * (AB_BN * 128) + (kk % 4) * 32;
+          umma_bf16(tmem_base + TM_S + buf * 128 + 64, make_smem_desc_sw128(sv + oa, 0, 1024),
+                    make_smem_desc_sw128(sdo + ob, 0, 1024), IDESC_S, kk != 0);
+        }
+      };
+      mbar_wait(big_full, 0);
+      if (n_steps > 0) {
+        mbar_wait(&sml_full[0], 0);
+        tc_fence_after();
+        issue_st_dpt(0, 0);
+        umma_commit(&s_full[0]);
+      }
+      int st = 0; uint32_t ph = 0;
+      for (int i = 0; i < n_steps; ++i) {
+        int st1 = st + 1; uint32_t ph1 = ph;
+        if (st1 == STAGES) { st1 = 0; ph1 ^= 1; }
+        if (i + 1 < n_steps) {
+          mbar_wait(&sml_full[st1], ph1);
+          tc_fence_after();
+          issue_st_dpt((i + 1) & 1, st1);
+          umma_commit(&s_full[(i + 1) & 1]);
+        }
+        mbar_wait(&t_ready[i & 1], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t spt = smem_u32(smem + S::OFF_T0 + (i & 1) * S::T_BYTES);
+        const uint32_t sdst = smem_u32(smem + S::OFF_T1 + (i & 1) * S::T_BYTES);
+        const uint32_t sq = smem_u32(smem + S::OFF_SML0 + st * S::SML_BYTES);
+        const uint32_t sdo = smem_u32(smem + S::OFF_SML1 + st * S::SML_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < AB_BN / 16; ++kk)
+          umma_bf16(tmem_base + TM_DV, make_smem_desc_sw128(spt + kk * 32, 0, 1024),
+                    make_smem_desc_sw128(sdo + kk * 2048, AB_BN * 128, 1024), IDESC_DKV, (i | kk) != 0);
+#pragma unroll
+        for (int kk = 0; kk < AB_BN / 16; ++kk)
+          umma_bf16(tmem_base + TM_DK, make_smem_desc_sw128(sdst + kk * 32, 0, 1024),
+                    make_smem_desc_sw128(sq + kk * 2048, AB_BN * 128, 1024), IDESC_DKV, (i | kk) != 0);
+        umma_commit(&sml_empty[st]);
+        st = st1; ph = ph1;
+      }
+      umma_commit(done);
+    }
+  } else {
+    // ---- math warpgroup: one thread per KEY row
+    const int quad = warp & 3;
+    const int r_in = quad * 32 + lane;
+    const int kv_row = kv0 + r_in;
+    const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16);
+    bool row_ok = kv_row < p.seq_kv;
+    const bool store_ok = row_ok;
+    if (row_ok && p.kv_mask) row_ok = p.kv_mask[int64_t(b) * p.seq_kv + kv_row] != 0;
+    const int sw = r_in & 7;
+    const int64_t stat_base = (int64_t(b) * p.nheads + head) * p.seq_q;
+    for (int i = 0; i < n_steps; ++i) {
+      const int buf = i & 1;
+      const int qt0 = (i_start + i) * AB_BN;
+      {  // stage lse / delta of this query tile (thread t<64: lse, t>=64: delta)
+        const int c = r_in & 63;
+        const int qi = qt0 + c;
+        float val;
+        if (r_in < 64) val = qi < p.seq_q ? p.lse[stat_base + qi] : INFINITY;
+        else val = qi < p.seq_q ? p.delta[stat_base + qi] : 0.f;
+        stats[buf * 128 + (r_in < 64 ? 0 : 64) + c] = val;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&s_full[buf], (i >> 1) & 1);
+      tc_fence_after();
+      const float* lse_s = stats + buf * 128;
+      const float* del_s = lse_s + 64;
+      uint8_t* spt = smem + S::OFF_T0 + buf * S::T_BYTES + r_in * 128;
+      uint8_t* sdst = smem + S::OFF_T1 + buf * S::T_BYTES + r_in * 128;
+      const bool need_causal = p.causal && (qt0 < kv0 + AB_BM - 1);
+#pragma unroll
+      for (int hc = 0; hc < 2; ++hc) {
+        uint32_t s[32], d[32];
+        tmem_ld32(t_lane + TM_S + buf * 128 + hc * 32, s);
+        tmem_ld32(t_lane + TM_S + buf * 128 + 64 + hc * 32, d);
+        tmem_ld_wait();
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int cc = hc * 32 + c + e;
+            float x = exp2f(__uint_as_float(s[c + e]) * p.scale_log2 - lse_s[cc]);
+            const bool keep = row_ok && !(need_causal && (qt0 + cc) < kv_row);
+            x = keep ? x : 0.f;
+            pv[e] = x;
+            dv[e] = x * (__uint_as_float(d[c + e]) - del_s[cc]);
+          }
+          pp[c >> 1] = pack_bf16x2(pv[0], pv[1]);
+          pd[c >> 1] = pack_bf16x2(dv[0], dv[1]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          *reinterpret_cast<uint4*>(spt + (((hc * 4 + ch) ^ sw) << 4)) =
+              make_uint4(pp[ch * 4], pp[ch * 4 + 1], pp[ch * 4 + 2], pp[ch * 4 + 3]);
+          *reinterpret_cast<uint4*>(sdst + (((hc * 4 + ch) ^ sw) << 4)) =
+              make_uint4(pd[ch * 4], pd[ch * 4 + 1], pd[ch * 4 + 2], pd[ch * 4 + 3]);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(&t_ready[buf]);
+    }
+    // ---- epilogue: dV, dK
+    mbar_wait(done, 0);
+    tc_fence_after();
+    __nv_bfloat16* dvp = p.dv + (int64_t(b) * p.seq_kv + kv_row) * p.dv_row_stride + int64_t(head) * p.dv_head_stride;
+    __nv_bfloat16* dkp = p.dk + (int64_t(b) * p.seq_kv + kv_row) * p.dk_row_stride + int64_t(head) * p.dk_head_stride;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+#pragma unroll
+      for (int ch = 0; ch < D / 32; ++ch) {
+        uint32_t t[32];
+        if (n_steps > 0) {
+          tmem_ld32(t_lane + (which == 0 ? TM_DV : TM_DK) + ch * 32, t);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) t[c] = 0u;
+        }
+        if (store_ok) {
+          const float mul = which == 0 ? 1.f : p.scale;
+          __nv_bfloat16* dst = (which == 0 ? dvp : dkp) + ch * 32;
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(t[c + e]) * mul;
+            *reinterpret_cast<uint4*>(dst + c) = pack8(f);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int D>
+static int launch_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                           int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, int64_t do_rs, int64_t o_hs,
+                           float* delta, AttBwdParams& p, cudaStream_t st) {
+  using S = AttBwdSmem<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      set_error("sdpa_bwd: cudaFuncSetAttribute(%d) failed", S::TOTAL);
+      return FSB_ERR_CUDA;
+    }
+    configured = true;
+  }
+  // 1. delta
+  {
+    const int64_t groups = int64_t(p.batch) * p.seq_q * p.nheads;
+    const int64_t threads = groups * (D / 8);
+    attn_delta_kernel<D><<<unsigned((threads + 255) / 256), 256, 0, st>>>(
+        (const __nv_bfloat16*)o, (const __nv_bfloat16*)dout, delta, o_rs, o_hs, do_rs, p.do_head_stride, p.batch, p.seq_q,
+        p.nheads);
+    FSB_CUDA_LAUNCH_CHECK();
+  }
+  CUtensorMap tq128, tdo128, tk64, tv64, tk128, tv128, tq64, tdo64;
+  int rc;
+  const int64_t wq = int64_t(p.nheads - 1) * p.q_head_stride + D, wk = int64_t(p.nheads - 1) * p.k_head_stride + D;
+  const int64_t wv = int64_t(p.nheads - 1) * p.v_head_stride + D, wdo = int64_t(p.nheads - 1) * p.do_head_stride + D;
+  if ((rc = make_attn_tmap(&tq128, q, q_rs, wq, p.seq_q, p.batch, AB_BM))) return rc;
+  if ((rc = make_attn_tmap(&tdo128, dout, do_rs, wdo, p.seq_q, p.batch, AB_BM))) return rc;
+  if ((rc = make_attn_tmap(&tk64, k, k_rs, wk, p.seq_kv, p.batch, AB_BN))) return rc;
+  if ((rc = make_attn_tmap(&tv64, v, v_rs, wv, p.seq_kv, p.batch, AB_BN))) return rc;
+  if ((rc = make_attn_tmap(&tk128, k, k_rs, wk, p.seq_kv, p.batch, AB_BM))) return rc;
+  if ((rc = make_attn_tmap(&tv128, v, v_rs, wv, p.seq_kv, p.batch, AB_BM))) return rc;
+  if ((rc = make_attn_tmap(&tq64, q, q_rs, wq, p.seq_q, p.batch, AB_BN))) return rc;
+  if ((rc = make_attn_tmap(&tdo64, dout, do_rs, wdo, p.seq_q, p.batch, AB_BN))) return rc;
+  // 2. dQ
+  {
+    dim3 grid((p.seq_q + AB_BM - 1) / AB_BM, p.nheads, p.batch);
+    attn_bwd_dq_kernel<D><<<grid, AB_THREADS, S::TOTAL, st>>>(tq128, tdo128, tk64, tv64, p);
+    FSB_CUDA_LAUNCH_CHECK();
+  }
+  // 3. dK, dV
+  {
+    dim3 grid((p.seq_kv + AB_BM - 1) / AB_BM, p.nheads, p.batch);
+    attn_bwd_dkv_kernel<D><<<grid, AB_THREADS, S::TOTAL, st>>>(tk128, tv128, tq64, tdo64, p);
+    FSB_CUDA_LAUNCH_CHECK();
+  }
+  return FSB_OK;
+}
+
+}  // namespace fsb
+
+using namespace fsb;
+
+extern "C" int fsb_sdpa_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                            const float* lse, float* delta, void* dq, void* dk, void* dv, int64_t batch, int64_t seq_q,
+                            int64_t seq_kv, int nheads, int head_dim, int64_t q_row_stride, int64_t k_row_stride,
+                            int64_t v_row_stride, int64_t o_row_stride, int64_t do_row_stride, int64_t dq_row_stride,
+                            int64_t dk_row_stride, int64_t dv_row_stride, int64_t q_head_stride, int64_t k_head_stride,
+                            int64_t v_head_stride, int64_t o_head_stride, int64_t do_head_stride,
+                            int64_t dq_head_stride, int64_t dk_head_stride, int64_t dv_head_stride, float scale,
+                            int causal, const uint8_t* kv_mask, fsb_stream_t st) {
+  FSB_REQUIRE(q && k && v && o && dout && lse && delta && dq && dk && dv, "sdpa_bwd: null pointer");
+  FSB_REQUIRE(head_dim == 64 || head_dim == 128, "sdpa_bwd: head_dim %d unsupported (64 or 128)", head_dim);
+  FSB_REQUIRE(batch > 0 && seq_q > 0 && seq_kv > 0 && nheads > 0 && batch < 65536 && nheads < 65536, "sdpa_bwd: bad dims");
+  FSB_REQUIRE(!causal || seq_q == seq_kv, "sdpa_bwd: causal needs seq_q == seq_kv");
+  FSB_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o) && aligned16(dout) && aligned16(dq) &&
+                  aligned16(dk) && aligned16(dv),
+              "sdpa_bwd: 16-byte alignment required");
+  FSB_REQUIRE((q_row_stride | k_row_stride | v_row_stride | o_row_stride | do_row_stride | dq_row_stride |
+               dk_row_stride | dv_row_stride | q_head_stride | k_head_stride | v_head_stride | o_head_stride |
+               do_head_stride | dq_head_stride | dk_head_stride | dv_head_stride) % 8 == 0,
+              "sdpa_bwd: strides must be multiples of 8 elements");
+  AttBwdParams p;
+  p.lse = lse; p.delta = delta; p.kv_mask = kv_mask;
+  p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
+  p.dq_row_stride = dq_row_stride; p.dk_row_stride = dk_row_stride; p.dv_row_stride = dv_row_stride;
+  p.dq_head_stride = dq_head_stride; p.dk_head_stride = dk_head_stride; p.dv_head_stride = dv_head_stride;
+  p.q_head_stride = int(q_head_stride); p.k_head_stride = int(k_head_stride); p.v_head_stride = int(v_head_stride);
+  p.do_head_stride = int(do_head_stride);
+  p.seq_q = int(seq_q); p.seq_kv = int(seq_kv); p.nheads = nheads; p.batch = int(batch); p.causal = causal;
+  p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
+  if (head_dim == 128)
+    return launch_attn_bwd<128>(q, k, v, o, dout, q_row_stride, k_row_stride, v_row_stride, o_row_stride, do_row_stride,
+                                o_head_stride, delta, p, (cudaStream_t)st);
+  return launch_attn_bwd<64>(q, k, v, o, dout, q_row_stride, k_row_stride, v_row_stride, o_row_stride, do_row_stride,
+                             o_head_stride, delta, p, (cudaStream_t)st);
+}

@@ -58,6 +58,8 @@ SIGNATURES = {
     "fsb_clip_coef": (c_int, [c_void_p, c_f32, c_void_p, c_void_p, c_void_p]),
     "fsb_sdpa_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int,
                              c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_void_p, c_void_p]),
+    "fsb_sdpa_bwd": (c_int, [c_void_p] * 10 + [c_i64, c_i64, c_i64, c_int, c_int] + [c_i64] * 16 +
+                     [c_f32, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -248,3 +248,21 @@ def sdpa_fwd(q, k, v, scale, causal, kv_mask=None, out=None):
     L.call("fsb_sdpa_fwd", _p(q), _p(k), _p(v), _p(out), _p(lse), B, Sq, Skv, H, D, q_rs, k_rs, v_rs, o_rs, q_hs, k_hs,
            v_hs, o_hs, float(scale), int(bool(causal)), _p(kv_mask), _stream())
     return out, lse
+
+
+def sdpa_bwd(q, k, v, out, dout, lse, scale, causal, dq, dk, dv, kv_mask=None):
+    """All tensors strided [B,S,H,D] bf16 views; dq/dk/dv are written (e.g. slices of a packed dQKV buffer)."""
+    B, Sq, H, D, q_rs, q_hs = _bshd(q, "q")
+    _, Skv, _, _, k_rs, k_hs = _bshd(k, "k")
+    _, _, _, _, v_rs, v_hs = _bshd(v, "v")
+    _, _, _, _, o_rs, o_hs = _bshd(out, "out")
+    _, _, _, _, do_rs, do_hs = _bshd(dout, "dout")
+    _, _, _, _, dq_rs, dq_hs = _bshd(dq, "dq")
+    _, _, _, _, dk_rs, dk_hs = _bshd(dk, "dk")
+    _, _, _, _, dv_rs, dv_hs = _bshd(dv, "dv")
+    for t, n in ((dout, "dout"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
+        _chk(t, _bf16, n)
+    delta = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
+    L.call("fsb_sdpa_bwd", _p(q), _p(k), _p(v), _p(out), _p(dout), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), B, Sq, Skv,
+           H, D, q_rs, k_rs, v_rs, o_rs, do_rs, dq_rs, dk_rs, dv_rs, q_hs, k_hs, v_hs, o_hs, do_hs, dq_hs, dk_hs, dv_hs,
+           float(scale), int(bool(causal)), _p(kv_mask), _stream())

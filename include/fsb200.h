@@ -87,6 +87,17 @@ int fsb_sdpa_fwd(const void* q, const void* k, const void* v, void* o, float* ls
                  int64_t q_head_stride, int64_t k_head_stride, int64_t v_head_stride, int64_t o_head_stride,
                  float scale, int causal, const uint8_t* kv_mask, fsb_stream_t stream);
 
+/* Backward of fsb_sdpa_fwd. o/lse are the forward outputs; delta: fp32 scratch [batch, nheads, seq_q] (written here);
+ * dq/dk/dv are written with their own strides (e.g. the three slices of a packed dQKV buffer). Deterministic. */
+int fsb_sdpa_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                 const float* lse, float* delta, void* dq, void* dk, void* dv,
+                 int64_t batch, int64_t seq_q, int64_t seq_kv, int nheads, int head_dim,
+                 int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride,
+                 int64_t do_row_stride, int64_t dq_row_stride, int64_t dk_row_stride, int64_t dv_row_stride,
+                 int64_t q_head_stride, int64_t k_head_stride, int64_t v_head_stride, int64_t o_head_stride,
+                 int64_t do_head_stride, int64_t dq_head_stride, int64_t dk_head_stride, int64_t dv_head_stride,
+                 float scale, int causal, const uint8_t* kv_mask, fsb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,59 @@ def test_sdpa_fwd(B, S, H, D, causal, layout):
     assert h == out.shape[2] * out.shape[3]
 
 
+@pytest.mark.parametrize("B,S,H,D,causal,layout", [
+    (2, 256, 2, 128, True, "llama"),
+    (1, 512, 2, 128, True, "llama"),
+    (2, 200, 2, 64, True, "gpt2"),
+    (2, 384, 2, 64, False, "gpt2"),
+    (1, 1024, 1, 64, True, "gpt2"),
+    (1, 2048, 1, 128, True, "llama"),
+    (3, 77, 2, 64, False, "gpt2"),
+])
+def test_sdpa_bwd(B, S, H, D, causal, layout):
+    g = torch.Generator().manual_seed(0)
+    if layout == "llama":
+        qkv = torch.randn(B, S, H, 3, D, generator=g).to(torch.bfloat16).to(DEV)
+        sel = lambda t, i: t[:, :, :, i]
+    else:
+        qkv = torch.randn(B, S, 3, H, D, generator=g).to(torch.bfloat16).to(DEV)
+        sel = lambda t, i: t[:, :, i]
+    q, k, v = sel(qkv, 0), sel(qkv, 1), sel(qkv, 2)
+    scale = 1.0 / math.sqrt(D)
+    out, lse = ops.sdpa_fwd(q, k, v, scale, causal)
+    dout = torch.randn(B, S, H, D, generator=g).to(torch.bfloat16).to(DEV)
+    dqkv = torch.full_like(qkv, float("nan"))
+    ops.sdpa_bwd(q, k, v, out, dout, lse, scale, causal, sel(dqkv, 0), sel(dqkv, 1), sel(dqkv, 2))
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ref, _ = _ref_attention(qf, kf, vf, scale, causal)
+    ref.backward(dout.float())
+    assert not torch.isnan(dqkv.float()).any(), "unwritten gradient elements"
+    for name, got, want in (("dq", sel(dqkv, 0), qf.grad), ("dk", sel(dqkv, 1), kf.grad), ("dv", sel(dqkv, 2), vf.grad)):
+        err = (got.float() - want).abs().max().item()
+        tol = 3e-2 * max(1.0, want.abs().max().item())  # P, dS rounded to bf16 before the second GEMMs
+        assert err < tol, f"{name}: max err {err} (tol {tol})"
+
+
+def test_sdpa_bwd_padding_mask():
+    B, S, H, D = 2, 320, 2, 64
+    g = torch.Generator().manual_seed(1)
+    qkv = torch.randn(B, S, 3, H, D, generator=g).to(torch.bfloat16).to(DEV)
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    mask = torch.ones(B, S, dtype=torch.uint8, device=DEV)
+    mask[0, 250:] = 0
+    mask[1, 17:40] = 0
+    out, lse = ops.sdpa_fwd(q, k, v, 0.125, False, kv_mask=mask)
+    dout = torch.randn(B, S, H, D, generator=g).to(torch.bfloat16).to(DEV)
+    dqkv = torch.zeros_like(qkv)
+    ops.sdpa_bwd(q, k, v, out, dout, lse, 0.125, False, dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], kv_mask=mask)
+    qf, kf, vf = (t.float().detach().requires_grad_(True) for t in (q, k, v))
+    ref, _ = _ref_attention(qf, kf, vf, 0.125, False, mask)
+    ref.backward(dout.float())
+    for got, want in ((dqkv[:, :, 0], qf.grad), (dqkv[:, :, 1], kf.grad), (dqkv[:, :, 2], vf.grad)):
+        assert (got.float() - want).abs().max().item() < 3e-2 * max(1.0, want.abs().max().item())
+
+
 def test_sdpa_fwd_padding_mask():
     B, S, H, D = 2, 320, 2, 64
     g = torch.Generator().manual_seed(1)
