@@ -167,6 +167,17 @@ __global__ void __launch_bounds__(256) add_kernel(const uint4* __restrict__ a, c
   }
 }
 
+// acc (fp32) += scale * x (bf16)   — gradient accumulation into the fp32 shard (ZeRO-2 per-micro-step reduce)
+__global__ void __launch_bounds__(256) accumulate_kernel(float* __restrict__ acc, const uint2* __restrict__ x,
+                                                         int64_t nvec, float scale, int overwrite) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nvec; i += int64_t(gridDim.x) * blockDim.x) {
+    const uint2 q = x[i];
+    float4 a = overwrite ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(acc)[i];
+    a.x += scale * bf16lo(q.x); a.y += scale * bf16hi(q.x); a.z += scale * bf16lo(q.y); a.w += scale * bf16hi(q.y);
+    reinterpret_cast<float4*>(acc)[i] = a;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- embedding
 // out[t] = W[ids[t]] (+ P[pos[t]]) (+ T[tt[t]]);   pos == nullptr with P != nullptr means pos[t] = t % seq_len.
 __global__ void __launch_bounds__(256) embedding_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ pos,
@@ -292,6 +303,13 @@ extern "C" int fsb_act_bwd(int act, const void* dy, const void* x, void* dx, int
 extern "C" int fsb_add(const void* a, const void* b, void* out, int64_t n, fsb_stream_t st) {
   FSB_REQUIRE(a && b && out && n > 0 && n % 8 == 0 && aligned16(a) && aligned16(b) && aligned16(out), "add: bad args");
   add_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, n / 8);
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+extern "C" int fsb_accumulate(float* acc, const void* x, int64_t n, float scale, int overwrite, fsb_stream_t st) {
+  FSB_REQUIRE(acc && x && n > 0 && n % 4 == 0 && aligned16(acc) && (reinterpret_cast<uintptr_t>(x) & 7) == 0,
+              "accumulate: bad args (n %% 4 == 0, aligned)");
+  accumulate_kernel<<<ew_grid(n / 4, 256), 256, 0, (cudaStream_t)st>>>(acc, (const uint2*)x, n / 4, scale, overwrite);
   FSB_CUDA_LAUNCH_CHECK();
   return FSB_OK;
 }

@@ -1,0 +1,99 @@
+"""Flat, bucketed parameter / gradient storage shared by the models and the ZeRO engine.
+
+All 16-bit parameters live in ONE contiguous bf16 buffer (gradients in a parallel buffer) — the layout DeepSpeed's
+ZeRO-1/2 optimizer creates by flattening — cut into BUCKETS (one per transformer layer, plus
+embeddings, LM head and one bucket for every no-weight-decay parameter). Each bucket is padded to a multiple of
+world_size*ALIGN so that data-parallel rank r owns the r-th equal slice of EVERY bucket:
+  * a bucket's gradients can be reduce-scattered the moment its layer's backward finishes (overlap with backward);
+  * the rank's optimizer state is the concatenation of its bucket slices (a contiguous local fp32 shard);
+  * after the update each bucket is re-assembled with one in-place all-gather.
+A bucket is homogeneous in weight decay (the grouping BY NAME of fengshen/models/model_utils.py:39-47), so the fused
+AdamW kernel runs once per bucket slice.
+"""
+import torch
+
+NO_DECAY_SUBSTRINGS = ['bias', 'LayerNorm.bias', 'LayerNorm.weight', 'layer_norm.', 'layernorm.']  # model_utils.py:40
+ALIGN = 128  # elements: every parameter starts 256-byte aligned (TMA needs 16 B, vector kernels 16 B)
+NO_DECAY_BUCKET = "no_decay"
+
+
+def is_no_decay(name):
+    return any(nd in name for nd in NO_DECAY_SUBSTRINGS)
+
+
+def _numel(shape):
+    n = 1
+    for s in shape:
+        n *= s
+    return n
+
+
+class FlatSpec:
+    """Ordered list of (name, shape, bucket). Entries of one bucket are laid out adjacently in registration order."""
+
+    def __init__(self):
+        self.entries = []
+
+    def add(self, name, shape, bucket):
+        self.entries.append((name, tuple(shape), NO_DECAY_BUCKET if is_no_decay(name) else bucket))
+
+    def plan(self, world_size=1):
+        """-> (offsets {name: (offset, shape)}, buckets [(bucket, start, length, weight_decay_on)], total)."""
+        order = []
+        for _, _, b in self.entries:
+            if b not in order and b != NO_DECAY_BUCKET:
+                order.append(b)
+        if any(b == NO_DECAY_BUCKET for _, _, b in self.entries):
+            order.append(NO_DECAY_BUCKET)
+        gran = world_size * ALIGN
+        offsets, buckets, cur = {}, [], 0
+        for b in order:
+            start = cur
+            for name, shape, bb in self.entries:
+                if bb != b:
+                    continue
+                offsets[name] = (cur, shape)
+                cur += (_numel(shape) + ALIGN - 1) // ALIGN * ALIGN
+            cur = start + (cur - start + gran - 1) // gran * gran
+            buckets.append((b, start, cur - start, b != NO_DECAY_BUCKET))
+        return offsets, buckets, cur
+
+
+class FlatBuffers:
+    """Owns the flat bf16 parameter and gradient buffers and hands out views."""
+
+    def __init__(self, spec, device, world_size=1, grad_dtype=torch.bfloat16):
+        self.offsets, self.buckets, self.total = spec.plan(world_size)
+        self.world_size = world_size
+        self.params = torch.zeros(self.total, dtype=torch.bfloat16, device=device)
+        self.grads = torch.zeros(self.total, dtype=grad_dtype, device=device)
+        self.bucket_index = {b: i for i, (b, _, _, _) in enumerate(self.buckets)}
+        # local shard layout: concatenation of this rank's slice of every bucket
+        self.shard_offsets, cur = [], 0
+        for _, _, length, _ in self.buckets:
+            self.shard_offsets.append(cur)
+            cur += length // world_size
+        self.shard_numel = cur
+
+    def view(self, name, grad=False):
+        off, shape = self.offsets[name]
+        buf = self.grads if grad else self.params
+        return buf[off:off + _numel(shape)].view(shape)
+
+    def span(self, first_name, rows, cols, grad=False):
+        """[rows, cols] view starting at `first_name` and covering the adjacent entries after it (fused GEMM operand)."""
+        off, _ = self.offsets[first_name]
+        buf = self.grads if grad else self.params
+        return buf[off:off + rows * cols].view(rows, cols)
+
+    def bucket_slice(self, i, rank, grad=False):
+        """Rank `rank`'s slice of bucket i inside the flat buffer."""
+        _, start, length, _ = self.buckets[i]
+        per = length // self.world_size
+        buf = self.grads if grad else self.params
+        return buf[start + rank * per: start + (rank + 1) * per]
+
+    def bucket_view(self, i, grad=False):
+        _, start, length, _ = self.buckets[i]
+        buf = self.grads if grad else self.params
+        return buf[start:start + length]

@@ -46,6 +46,7 @@ SIGNATURES = {
     "fsb_act_fwd": (c_int, [c_int, c_void_p, c_void_p, c_i64, c_void_p]),
     "fsb_act_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "fsb_add": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "fsb_accumulate": (c_int, [c_void_p, c_void_p, c_i64, c_f32, c_int, c_void_p]),
     "fsb_embedding_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64,
                                   c_i64, c_void_p]),
     "fsb_embedding_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),

@@ -1,0 +1,281 @@
+"""Ziya-LLaMA on the fsb200 kernels — drop-in for `fengshen.models.llama.modeling_llama.LlamaForCausalLM`.
+
+Same constructor (`LlamaForCausalLM(config)`), same `forward(input_ids, attention_mask, position_ids, labels)` ->
+`CausalLMOutputWithPast`-like result (reference: fengshen/models/llama/modeling_llama.py:272-351), same state-dict key
+names (`llama.embed_in.word_embeddings.weight`, `llama.layers.N.attention.query_key_value.weight`, ...,
+`embed_out.final_linear.weight`; utils/llama_convert/hf_to_fs.py:136-147), same per-head interleaved QKV weight layout
+(layers/transformer.py:488-497). What differs is everything underneath:
+  * activations stay [b, s, h] token-major — no [s, b, h] transposes (modeling_llama.py:201,222), no q/k/v repacking;
+  * all parameters are views into one flat bf16 buffer, gradients go straight into the parallel flat grad buffer;
+  * the whole network is ONE autograd node (`_LlamaStep`): forward runs the hand-scheduled kernel sequence and keeps
+    the activations it needs; `loss.backward()` runs the matching hand-written backward (dgrad / wgrad GEMMs, fused
+    attention backward, norm backward with the residual-gradient add fused in).
+The causal mask is implicit (flash path semantics, transformer.py:441-448: `attention_mask` is not applied; identical to
+the `global` path when the mask is all ones — SURVEY.md Appendix B).
+"""
+import math
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+
+from .. import lib as L
+from .. import ops
+from ..flat import FlatBuffers, FlatSpec
+
+
+def llama_ff_dim(hidden_size, multiple_of=256):
+    ff = int(2 * hidden_size * 4 / 3)  # layers/transformer.py:589-590
+    return multiple_of * ((ff + multiple_of - 1) // multiple_of)
+
+
+class _Holder(nn.Module):
+    """Bare container so that named_parameters()/state_dict() reproduce the reference's key names."""
+
+
+def _init_normal_(t, std, gen):
+    t.copy_(torch.empty(t.shape, dtype=torch.float32).normal_(0.0, std, generator=gen).to(t.dtype))
+
+
+class LlamaForCausalLM(nn.Module):
+    def __init__(self, config, device=None, world_size=1, seed=0):
+        super().__init__()
+        self.config = config
+        dev = torch.device(device if device is not None else "cuda")
+        if dev.type != "cuda":
+            raise RuntimeError("fsb200 LlamaForCausalLM runs on CUDA only (no CPU fallback on the product path)")
+        h, V, nl, nh = config.hidden_size, config.vocab_size, config.num_hidden_layers, config.num_attention_heads
+        self.h, self.V, self.nl, self.nh = h, V, nl, nh
+        self.hn = h // nh
+        self.ff = llama_ff_dim(h, getattr(config, "llama_mlp_multiple_of", 256))
+        self.eps = getattr(config, "rms_norm_epsilon", 1e-6)
+        if self.hn not in (64, 128):
+            raise RuntimeError(f"fsb200: head dim {self.hn} unsupported (64 or 128)")
+        if V % 8 or h % 8:
+            raise RuntimeError("fsb200: vocab_size and hidden_size must be multiples of 8")
+
+        spec = FlatSpec()
+        spec.add("llama.embed_in.word_embeddings.weight", (V, h), "embed_in")
+        for i in range(nl):
+            p, bk = f"llama.layers.{i}.", f"layer{i}"
+            spec.add(p + "input_layernorm.scale", (h,), bk)          # *.scale names match 'layernorm.' -> no-decay bucket
+            spec.add(p + "attention.query_key_value.weight", (3 * h, h), bk)
+            spec.add(p + "attention.dense.weight", (h, h), bk)
+            spec.add(p + "post_attention_layernorm.scale", (h,), bk)
+            spec.add(p + "mlp.w1.weight", (self.ff, h), bk)   # w1 | w3 adjacent: one [2ff, h] GEMM operand
+            spec.add(p + "mlp.w3.weight", (self.ff, h), bk)
+            spec.add(p + "mlp.w2.weight", (h, self.ff), bk)
+        spec.add("llama.final_layer_norm.scale", (h,), "head")
+        spec.add("embed_out.final_linear.weight", (V, h), "head")
+        self.flat = FlatBuffers(spec, dev, world_size=world_size)
+
+        # module tree mirroring the reference (modeling_llama.py:97-127, :239-252)
+        def P(name):
+            prm = nn.Parameter(self.flat.view(name), requires_grad=True)
+            prm.main_grad = self.flat.view(name, grad=True)
+            prm.fsb_name = name
+            return prm
+
+        self.llama = _Holder()
+        self.llama.embed_in = _Holder()
+        self.llama.embed_in.word_embeddings = _Holder()
+        self.llama.embed_in.word_embeddings.weight = P("llama.embed_in.word_embeddings.weight")
+        self.llama.layers = nn.ModuleList()
+        inv_freq = 1.0 / (getattr(config, "rotary_emb_base", 10000) ** (torch.arange(0, self.hn, 2).float() / self.hn))
+        for i in range(nl):
+            p = f"llama.layers.{i}."
+            lyr = _Holder()
+            lyr.input_layernorm = _Holder(); lyr.input_layernorm.scale = P(p + "input_layernorm.scale")
+            lyr.attention = _Holder()
+            lyr.attention.query_key_value = _Holder()
+            lyr.attention.query_key_value.weight = P(p + "attention.query_key_value.weight")
+            lyr.attention.rotary_emb = _Holder()
+            lyr.attention.rotary_emb.register_buffer("inv_freq", inv_freq.clone().to(dev))
+            lyr.attention.dense = _Holder(); lyr.attention.dense.weight = P(p + "attention.dense.weight")
+            lyr.post_attention_layernorm = _Holder()
+            lyr.post_attention_layernorm.scale = P(p + "post_attention_layernorm.scale")
+            lyr.mlp = _Holder()
+            lyr.mlp.w1 = _Holder(); lyr.mlp.w1.weight = P(p + "mlp.w1.weight")
+            lyr.mlp.w3 = _Holder(); lyr.mlp.w3.weight = P(p + "mlp.w3.weight")
+            lyr.mlp.w2 = _Holder(); lyr.mlp.w2.weight = P(p + "mlp.w2.weight")
+            lyr.w13 = None  # filled below (non-parameter view)
+            self.llama.layers.append(lyr)
+        self.llama.final_layer_norm = _Holder()
+        self.llama.final_layer_norm.scale = P("llama.final_layer_norm.scale")
+        self.embed_out = _Holder()
+        self.embed_out.final_linear = _Holder()
+        self.embed_out.final_linear.weight = P("embed_out.final_linear.weight")
+
+        self._w13 = [self.flat.span(f"llama.layers.{i}.mlp.w1.weight", 2 * self.ff, h)
+                     for i in range(nl)]
+        self._dw13 = [self.flat.span(f"llama.layers.{i}.mlp.w1.weight", 2 * self.ff, h, grad=True) for i in range(nl)]
+
+        # RoPE tables exactly as RotaryEmbedding builds them (layers/positional_embeddings.py:38-52), fp32
+        max_pos = getattr(config, "max_position_embeddings", 2048)
+        t = torch.arange(max_pos, dtype=inv_freq.dtype)
+        freqs = torch.einsum("i,j->ij", t, inv_freq)
+        self.register_buffer("_cos", freqs.cos().contiguous().to(dev), persistent=False)
+        self.register_buffer("_sin", freqs.sin().contiguous().to(dev), persistent=False)
+
+        self.reset_parameters(seed)
+        self.accumulate_grads = False   # set by the engine for micro-batches after the first
+        self.loss_scale = 1.0           # 1 / (gradient_accumulation_steps * world_size), folded into dlogits
+        self.grad_hook = None           # engine callback: grad_hook(bucket_name) when a bucket's gradients are final
+
+    # ---- init (layers/init_functions.py:121-142: small_init std sqrt(2/(5h)); wang_init std 2/(L*sqrt(h))) -------------
+    @torch.no_grad()
+    def reset_parameters(self, seed=0):
+        gen = torch.Generator().manual_seed(seed)
+        h, nl = self.h, self.nl
+        small = math.sqrt(2.0 / (5.0 * h))
+        wang = 2.0 / (nl * math.sqrt(h))
+        for name, prm in self.named_parameters():
+            if name.endswith(".scale"):
+                prm.fill_(1.0)
+            elif name.endswith("dense.weight") or name.endswith("w2.weight"):
+                _init_normal_(prm.data, wang, gen)
+            else:
+                _init_normal_(prm.data, small, gen)
+
+    # HF-style loading of a reference state dict (fp32/fp16/bf16 tensors on any device)
+    @torch.no_grad()
+    def load_reference_state_dict(self, sd):
+        own = dict(self.named_parameters())
+        missing = [k for k in own if k not in sd]
+        if missing:
+            raise KeyError(f"missing keys in state dict: {missing[:4]}...")
+        for k, prm in own.items():
+            if tuple(sd[k].shape) != tuple(prm.shape):
+                raise ValueError(f"shape mismatch for {k}: {tuple(sd[k].shape)} vs {tuple(prm.shape)}")
+            prm.copy_(sd[k].to(device=prm.device, dtype=prm.dtype))
+
+    # ---- forward ----------------------------------------------------------------------------------------------------
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, labels=None, return_logits=False, **_):
+        B, S = input_ids.shape
+        dev = self.flat.params.device
+        ids = input_ids.to(device=dev, dtype=torch.int64).contiguous().view(-1)
+        if position_ids is None:
+            pos = torch.arange(S, device=dev, dtype=torch.int64).repeat(B)
+        else:
+            pos = position_ids.to(device=dev, dtype=torch.int64).expand(B, S).contiguous().view(-1)
+        lab = None if labels is None else labels.to(device=dev, dtype=torch.int64).contiguous().view(-1)
+        if lab is not None and torch.is_grad_enabled():
+            # a leaf that requires grad makes the node differentiable; real gradients go to the flat grad buffer
+            loss, logits = _LlamaStep.apply(self, ids, pos, lab, B, S, return_logits,
+                                            self.llama.final_layer_norm.scale)
+        else:
+            loss, logits, _ = self._forward_impl(ids, pos, lab, B, S, save=False, want_logits=True)
+        return SimpleNamespace(loss=loss, logits=None if logits is None else logits.view(B, S, self.V),
+                               past_key_values=None, hidden_states=None, attentions=None)
+
+    def _forward_impl(self, ids, pos, lab, B, S, save, want_logits):
+        h, nh, hn, ff = self.h, self.nh, self.hn, self.ff
+        T = B * S
+        acts = []
+        x = ops.embedding_fwd(ids, self.llama.embed_in.word_embeddings.weight.data)
+        prev_m = None
+        for i, lyr in enumerate(self.llama.layers):
+            h1, rstd1, x = ops.rmsnorm_fwd(x if prev_m is None else prev_m, lyr.input_layernorm.scale.data, self.eps,
+                                           residual=None if prev_m is None else x)
+            qkv = ops.gemm(L.GEMM_NT, h1, lyr.attention.query_key_value.weight.data)
+            ops.rope_inplace(qkv, self._cos, self._sin, pos, nh, hn, 3 * h, 3 * hn, offset=0)
+            ops.rope_inplace(qkv, self._cos, self._sin, pos, nh, hn, 3 * h, 3 * hn, offset=hn)
+            q5 = qkv.view(B, S, nh, 3, hn)
+            o, lse = ops.sdpa_fwd(q5[:, :, :, 0], q5[:, :, :, 1], q5[:, :, :, 2], 1.0 / math.sqrt(hn), True)
+            o2 = o.view(T, h)
+            a = ops.gemm(L.GEMM_NT, o2, lyr.attention.dense.weight.data)
+            h2, rstd2, x1 = ops.rmsnorm_fwd(a, lyr.post_attention_layernorm.scale.data, self.eps, residual=x)
+            gu = ops.gemm(L.GEMM_NT, h2, self._w13[i])
+            act = ops.glu_fwd(L.ACT_SILU, gu[:, :ff], gu[:, ff:])
+            m = ops.gemm(L.GEMM_NT, act, lyr.mlp.w2.weight.data)
+            if save:
+                acts.append((x, rstd1, h1, qkv, o, lse, x1, rstd2, h2, gu, act))
+            x, prev_m = x1, m
+        hf, rstdf, xf = ops.rmsnorm_fwd(prev_m, self.llama.final_layer_norm.scale.data, self.eps, residual=x)
+        logits = ops.gemm(L.GEMM_NT, hf, self.embed_out.final_linear.weight.data)
+        loss = None
+        ctx = None
+        if lab is not None:
+            keep = logits.clone() if (want_logits and save) else None
+            loss, dlogits, _ = ops.softmax_xent(logits, lab, S, shift=1, grad_scale=self.loss_scale,
+                                                dlogits="inplace" if save else None)
+            if save:
+                ctx = (acts, hf, rstdf, xf, dlogits, ids, pos, B, S)
+                logits = keep
+        return loss, (logits if want_logits else None), ctx
+
+    # ---- backward ---------------------------------------------------------------------------------------------------
+    def _backward_impl(self, ctx, gloss):
+        acts, hf, rstdf, xf, dlogits, ids, pos, B, S = ctx
+        h, nh, hn, ff = self.h, self.nh, self.hn, self.ff
+        T = B * S
+        acc = self.accumulate_grads
+        if gloss is not None:
+            dlogits.mul_(gloss.to(dlogits.dtype))  # upstream scalar (normally 1.0); host plumbing, off the hot path
+        W_out = self.embed_out.final_linear.weight
+        dhf = ops.gemm(L.GEMM_NN, dlogits, W_out.data)
+        ops.gemm(L.GEMM_TN, dlogits, hf, out=W_out.main_grad, accumulate=acc)
+        del dlogits
+        self._done("head")
+        fscale = self.llama.final_layer_norm.scale
+        dx = ops.rmsnorm_bwd(dhf, xf, fscale.data, rstdf, fscale.main_grad, accumulate=acc)
+        for i in reversed(range(self.nl)):
+            lyr = self.llama.layers[i]
+            x, rstd1, h1, qkv, o, lse, x1, rstd2, h2, gu, act = acts[i]
+            acts[i] = None
+            # x_next = x1 + m  ->  dm = dx, residual gradient into x1 = dx
+            w2 = lyr.mlp.w2.weight
+            dact = ops.gemm(L.GEMM_NN, dx, w2.data)
+            ops.gemm(L.GEMM_TN, dx, act, out=w2.main_grad, accumulate=acc)
+            dgu = torch.empty_like(gu)
+            ops.glu_bwd(L.ACT_SILU, dact, gu[:, :ff], gu[:, ff:], dgu[:, :ff], dgu[:, ff:])
+            dh2 = ops.gemm(L.GEMM_NN, dgu, self._w13[i])
+            ops.gemm(L.GEMM_TN, dgu, h2, out=self._dw13[i], accumulate=acc)
+            s2 = lyr.post_attention_layernorm.scale
+            dx1 = ops.rmsnorm_bwd(dh2, x1, s2.data, rstd2, s2.main_grad, accumulate=acc, dres=dx)
+            # x1 = x + a  ->  da = dx1
+            wd = lyr.attention.dense.weight
+            do = ops.gemm(L.GEMM_NN, dx1, wd.data)
+            ops.gemm(L.GEMM_TN, dx1, o.view(T, h), out=wd.main_grad, accumulate=acc)
+            dqkv = torch.empty_like(qkv)
+            q5, d5 = qkv.view(B, S, nh, 3, hn), dqkv.view(B, S, nh, 3, hn)
+            ops.sdpa_bwd(q5[:, :, :, 0], q5[:, :, :, 1], q5[:, :, :, 2], o, do.view(B, S, nh, hn), lse,
+                         1.0 / math.sqrt(hn), True, d5[:, :, :, 0], d5[:, :, :, 1], d5[:, :, :, 2])
+            ops.rope_inplace(dqkv, self._cos, self._sin, pos, nh, hn, 3 * h, 3 * hn, backward=True, offset=0)
+            ops.rope_inplace(dqkv, self._cos, self._sin, pos, nh, hn, 3 * h, 3 * hn, backward=True, offset=hn)
+            wq = lyr.attention.query_key_value.weight
+            dh1 = ops.gemm(L.GEMM_NN, dqkv, wq.data)
+            ops.gemm(L.GEMM_TN, dqkv, h1, out=wq.main_grad, accumulate=acc)
+            s1 = lyr.input_layernorm.scale
+            dx = ops.rmsnorm_bwd(dh1, x, s1.data, rstd1, s1.main_grad, accumulate=acc, dres=dx1)
+            self._done(f"layer{i}")
+        W_in = self.llama.embed_in.word_embeddings.weight
+        if not acc:
+            W_in.main_grad.zero_()
+        ops.embedding_bwd(ids, dx, W_in.main_grad)
+        self._done("embed_in")
+        self._done("no_decay")
+
+    def _done(self, bucket):
+        if self.grad_hook is not None:
+            self.grad_hook(bucket)
+
+
+class _LlamaStep(torch.autograd.Function):
+    """The whole network as one autograd node; `flat_params` is the differentiable handle (its .grad is never
+    materialised: gradients are written into model.flat.grads by the kernels)."""
+
+    @staticmethod
+    def forward(ctx, model, ids, pos, lab, B, S, want_logits, flat_params):
+        loss, logits, saved = model._forward_impl(ids, pos, lab, B, S, save=True, want_logits=want_logits)
+        ctx.model = model
+        ctx.saved = saved
+        ctx.mark_non_differentiable(*([logits] if logits is not None else []))
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, gloss, _glogits):
+        model, saved = ctx.model, ctx.saved
+        ctx.saved = None
+        model._backward_impl(saved, None if gloss is None else gloss)
+        return (None,) * 8

@@ -171,6 +171,11 @@ def add(a, b, out=None):
     return out
 
 
+def accumulate(acc32, x16, scale=1.0, overwrite=False):
+    """acc32 (fp32) = (0 if overwrite else acc32) + scale * x16 (bf16)."""
+    L.call("fsb_accumulate", _p(acc32), _p(x16), acc32.numel(), float(scale), int(bool(overwrite)), _stream())
+
+
 def embedding_fwd(ids, W, pos=None, P=None, token_type=None, T=None, seq_len=1):
     rows = ids.numel()
     cols = W.shape[1]
