@@ -178,6 +178,61 @@ __global__ void __launch_bounds__(256) accumulate_kernel(float* __restrict__ acc
   }
 }
 
+// Column sums of a bf16 matrix x[rows, cols] (row stride ld): bias gradients db[n] = sum_t dy[t, n], and the learned
+// position-embedding gradient dP[s,:] = sum_b dx[b,s,:] (view x as [B, S*h]). Stage 1: each CTA sums a strip of rows for
+// a 256-column tile (8 columns per thread, 32 row-lanes) -> partial[strip, cols] fp32; stage 2 reduces the strips.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial,
+                                                          int64_t rows, int cols, int64_t ld, int rows_per_strip) {
+  __shared__ float sm[8][64 + 1];  // [row-lane][col within tile]; 8 lanes x 64 cols per CTA
+  const int cl = threadIdx.x & 7;        // 8 threads x 8 cols = 64 columns per CTA
+  const int rl = threadIdx.x >> 3;       // 32 row lanes
+  const int col = blockIdx.x * 64 + cl * 8;
+  const int64_t r0 = int64_t(blockIdx.y) * rows_per_strip;
+  const int64_t r1 = min(rows, r0 + rows_per_strip);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < cols) {
+    for (int64_t r = r0 + rl; r < r1; r += 32) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + r * ld + col), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+  // reduce the 32 row lanes: first within each warp (4 row lanes per warp: lanes differ in bits 3,4), then via smem
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+    acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[w][cl * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < cols) partial[int64_t(blockIdx.y) * cols + c] = t;
+  }
+}
+__global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partial, void* __restrict__ out,
+                                                            int nparts, int cols, int out_f32, int accumulate) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  float t = 0.f;
+  for (int r = 0; r < nparts; ++r) t += partial[int64_t(r) * cols + c];
+  if (out_f32) {
+    float* o = reinterpret_cast<float*>(out);
+    o[c] = accumulate ? o[c] + t : t;
+  } else {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    o[c] = __float2bfloat16(accumulate ? __bfloat162float(o[c]) + t : t);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- embedding
 // out[t] = W[ids[t]] (+ P[pos[t]]) (+ T[tt[t]]);   pos == nullptr with P != nullptr means pos[t] = t % seq_len.
 __global__ void __launch_bounds__(256) embedding_fwd_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ pos,
@@ -303,6 +358,36 @@ extern "C" int fsb_act_bwd(int act, const void* dy, const void* x, void* dx, int
 extern "C" int fsb_add(const void* a, const void* b, void* out, int64_t n, fsb_stream_t st) {
   FSB_REQUIRE(a && b && out && n > 0 && n % 8 == 0 && aligned16(a) && aligned16(b) && aligned16(out), "add: bad args");
   add_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, n / 8);
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+static void colsum_plan(int64_t rows, int64_t cols, int& nstrips, int& rows_per_strip) {
+  const int col_tiles = int((cols + 63) / 64);
+  int64_t want = (int64_t(4) * num_sms() + col_tiles - 1) / col_tiles;
+  int64_t max_strips = (rows + 31) / 32;
+  if (want > max_strips) want = max_strips;
+  if (want < 1) want = 1;
+  if (want > 1024) want = 1024;
+  rows_per_strip = int(((rows + want - 1) / want + 31) / 32 * 32);
+  nstrips = int((rows + rows_per_strip - 1) / rows_per_strip);
+}
+extern "C" size_t fsb_colsum_workspace_bytes(int64_t rows, int64_t cols) {
+  int ns, rps;
+  colsum_plan(rows, cols, ns, rps);
+  return size_t(ns) * size_t(cols) * sizeof(float);
+}
+extern "C" int fsb_colsum(const void* x, int64_t rows, int64_t cols, int64_t ld, void* out, int out_dtype, int accumulate,
+                          void* workspace, size_t workspace_bytes, fsb_stream_t st) {
+  FSB_REQUIRE(x && out && workspace && rows > 0 && cols > 0 && cols % 8 == 0 && ld % 8 == 0 && aligned16(x),
+              "colsum: bad args (cols, ld multiples of 8; 16-byte aligned)");
+  int ns, rps;
+  colsum_plan(rows, cols, ns, rps);
+  FSB_REQUIRE(workspace_bytes >= size_t(ns) * cols * sizeof(float), "colsum: workspace too small");
+  dim3 grid(unsigned((cols + 63) / 64), unsigned(ns));
+  colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, (float*)workspace, rows, int(cols), ld, rps);
+  FSB_CUDA_LAUNCH_CHECK();
+  colsum_finish_kernel<<<unsigned((cols + 255) / 256), 256, 0, (cudaStream_t)st>>>((const float*)workspace, out, ns,
+                                                                                  int(cols), out_dtype == FSB_F32, accumulate);
   FSB_CUDA_LAUNCH_CHECK();
   return FSB_OK;
 }

@@ -176,6 +176,15 @@ def accumulate(acc32, x16, scale=1.0, overwrite=False):
     L.call("fsb_accumulate", _p(acc32), _p(x16), acc32.numel(), float(scale), int(bool(overwrite)), _stream())
 
 
+def colsum(x, out, accumulate=False):
+    """out[c] (+)= sum_r x[r, c]; x bf16 [rows, cols] (unit inner stride); out bf16 or fp32 [cols]."""
+    rows, cols, ld = _rows2d(x, "x")
+    nbytes = L.load().fsb_colsum_workspace_bytes(rows, cols)
+    ws = workspace(nbytes, x.device, "colsum")
+    L.call("fsb_colsum", _p(x), rows, cols, ld, _p(out), L.F32 if out.dtype == torch.float32 else L.BF16,
+           int(bool(accumulate)), _p(ws), ws.numel(), _stream())
+
+
 def embedding_fwd(ids, W, pos=None, P=None, token_type=None, T=None, seq_len=1):
     rows = ids.numel()
     cols = W.shape[1]

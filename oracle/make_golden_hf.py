@@ -1,0 +1,39 @@
+"""TEST INFRASTRUCTURE — writes tests/golden/gpt2_small.npz from transformers' own GPT2LMHeadModel (CPU, fp32, eager),
+the implementation the reference's GPT-2 script calls (examples/wenzhong_qa/finetune_wenzhong.py:56).
+Run:  python oracle/make_golden_hf.py      (records the transformers version it was generated with)"""
+import os
+import sys
+
+import numpy as np
+import torch
+import transformers
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import hf_oracle as H  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+STEPS, LR, WD = 20, 1e-3, 0.1
+
+
+def main():
+    torch.set_num_threads(os.cpu_count())
+    V = H.GPT2_SMALL["vocab_size"]
+    model = H.build_gpt2(H.GPT2_SMALL)
+    batch = H.make_lm_batch(V, 2, 96, seed=1234)
+    out = model(input_ids=batch["input_ids"], labels=batch["labels"])
+    out.loss.backward()
+    rec = {"loss": np.array(out.loss.item()), "logits_slice": out.logits.detach()[:, :, :64].numpy(),
+           "transformers_version": np.array(transformers.__version__)}
+    for n, p in model.named_parameters():
+        rec["gradnorm/" + n] = np.array(p.grad.norm().item())
+    model = H.build_gpt2(H.GPT2_SMALL)
+    batches = [H.make_lm_batch(V, 2, 96, seed=1234 + i) for i in range(4)]
+    rec["loss_curve"] = np.array(H.train_gpt2(model, batches, STEPS, lr=LR, weight_decay=WD, warmup=2))
+    rec["train_hparams"] = np.array([LR, 0.9, 0.999, 1e-8, WD])
+    np.savez_compressed(os.path.join(OUT, "gpt2_small.npz"), **rec)
+    print("gpt2_small: loss", out.loss.item(), "curve", rec["loss_curve"][0], "->", rec["loss_curve"][-1])
+
+
+if __name__ == "__main__":
+    main()
