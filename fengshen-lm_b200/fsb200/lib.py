@@ -99,10 +99,17 @@ def check(rc, what):
         raise RuntimeError(f"fsb200: {what} failed (status {rc}): {last_error()}")
 
 
+kernel_launches = 0  # number of __global__ launches issued by the library on behalf of this process
+# kernels launched per successful entry-point call (everything not listed launches exactly one)
+_KERNELS_PER_CALL = {"fsb_rmsnorm_bwd": 2, "fsb_layernorm_bwd": 2, "fsb_softmax_xent_fwd_bwd": 3, "fsb_sdpa_bwd": 3,
+                     "fsb_sumsq": 2, "fsb_colsum": 2}
+
+
 def call(name, *args):
     """Invoke a status-returning entry point and raise on error."""
-    global launch_count
+    global launch_count, kernel_launches
     launch_count += 1
+    kernel_launches += _KERNELS_PER_CALL.get(name, 1)
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"fsb200: {name} failed (status {rc}): {last_error()}")

@@ -75,10 +75,41 @@ def gemm(layout, a, b, out=None, out_dtype=_bf16, bias=None, epilogue=L.EPI_NONE
     if aux is not None:
         _chk(aux, _bf16, "aux")
         _, _, ldaux = _rows2d(aux, "aux")
+    prof = _profiler
+    if prof is not None:
+        ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
     L.call("fsb_gemm_bf16", layout, M, N, K, _p(a), lda, _p(b), ldb, _p(out), ldd,
            L.F32 if out.dtype == torch.float32 else L.BF16, _p(bias), bias_dt, epilogue, int(bool(accumulate)),
            _p(aux), ldaux, 1, 0, 0, 0, 0, _stream())
+    if prof is not None:
+        ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
+        prof.add("gemm_bf16_kernel", ev0, ev1, 2.0 * M * N * K)
     return out
+
+
+class KernelProfiler:
+    """CUDA-event timing of individual launches on the launching stream (bench.py's roofline block)."""
+
+    def __init__(self):
+        self.rec = {}
+
+    def add(self, name, ev0, ev1, work):
+        self.rec.setdefault(name, []).append((ev0, ev1, work))
+
+    def summary(self):
+        out = {}
+        for name, items in self.rec.items():
+            ms = sum(a.elapsed_time(b) for a, b, _ in items)
+            out[name] = {"launches": len(items), "ms": ms, "work": sum(w for _, _, w in items)}
+        return out
+
+
+_profiler = None
+
+
+def set_profiler(p):
+    global _profiler
+    _profiler = p
 
 
 # ------------------------------------------------------------------------------------------------------ norms
