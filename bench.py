@@ -217,12 +217,17 @@ def main():
     ap.add_argument("--workload", default="gpt2-110m")
     ap.add_argument("--impl", default="fsb200", choices=["fsb200", "reference"])
     ap.add_argument("--micro-batch", type=int, default=0)
+    ap.add_argument("--per-gpu-batch", type=int, default=0, help="override sequences per GPU per step (profiling only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     w = workload(args.workload)
     if args.micro_batch:
         w["micro"] = args.micro_batch
+    if args.per_gpu_batch:
+        w["per_gpu"] = args.per_gpu_batch
+        w["label"] += f" [per-GPU batch overridden to {args.per_gpu_batch}: profiling only]"
+    w["micro"] = min(w["micro"], w["per_gpu"])
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -83,6 +83,16 @@ class FlatBuffers:
     def span(self, first_name, rows, cols, grad=False):
         """[rows, cols] view starting at `first_name` and covering the adjacent entries after it (fused GEMM operand)."""
         off, _ = self.offsets[first_name]
+        covered, cur = 0, off
+        for name, (o, shape) in sorted(self.offsets.items(), key=lambda kv: kv[1][0]):
+            if o < off or covered >= rows * cols:
+                continue
+            if o != cur:
+                raise ValueError(f"span({first_name}): entries are not contiguous at {name} (padding in between)")
+            covered += _numel(shape)
+            cur = o + _numel(shape)
+        if covered != rows * cols:
+            raise ValueError(f"span({first_name}): {rows}x{cols} does not end on a parameter boundary")
         buf = self.grads if grad else self.params
         return buf[off:off + rows * cols].view(rows, cols)
 

@@ -72,6 +72,86 @@ int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K,
                   int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_d, int64_t stride_aux,
                   fsb_stream_t stream);
 
+/* ---- RMSNorm / LayerNorm ------------------------------------------------------------------------------------
+ * RMSNorm.forward fengshen/models/megatron/layers/norms.py:44-52 (y = scale * cast(x * rsqrt(mean(x^2) + eps)), the cast to
+ * 16 bit happening BEFORE the scale multiply); LayerNorm = torch.nn.LayerNorm (norms.py:16; HF BERT/GPT-2 eps 1e-12/1e-5).
+ * x, y, residual, sum_out, dy, dx, dres: bf16 [rows, cols] contiguous; cols % 8 == 0, cols <= 16384. scale/gamma/beta bf16.
+ * residual != NULL fuses x_sum = x + residual (written to sum_out, which the norm then reads) — the residual adds of
+ * ParallelTransformerLayer.forward (layers/transformer.py:775-788). dres != NULL fuses dx += dres in backward.
+ * stats: fp32 [rows] (rstd) for RMSNorm, [rows][2] (mean, rstd) for LayerNorm. Weight gradients (bf16 or fp32 per
+ * wgrad_dtype, optionally accumulated) are reduced deterministically through `workspace` (fsb_norm_bwd_workspace_bytes). */
+size_t fsb_norm_bwd_workspace_bytes(int64_t rows, int64_t cols, int is_layernorm);
+int fsb_rmsnorm_fwd(const void* x, const void* residual, const void* scale, void* y, void* sum_out, float* rstd,
+                    int64_t rows, int64_t cols, float eps, fsb_stream_t stream);
+int fsb_rmsnorm_bwd(const void* dy, const void* x, const void* scale, const float* rstd, const void* dres, void* dx,
+                    void* dscale, int wgrad_dtype, int accumulate, void* workspace, size_t workspace_bytes,
+                    int64_t rows, int64_t cols, fsb_stream_t stream);
+int fsb_layernorm_fwd(const void* x, const void* residual, const void* gamma, const void* beta, void* y, void* sum_out,
+                      float* mean_rstd, int64_t rows, int64_t cols, float eps, fsb_stream_t stream);
+int fsb_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean_rstd, const void* dres,
+                      void* dx, void* dgamma, void* dbeta, int wgrad_dtype, int accumulate, void* workspace,
+                      size_t workspace_bytes, int64_t rows, int64_t cols, fsb_stream_t stream);
+
+/* ---- rotary embedding, in place -----------------------------------------------------------------------------
+ * apply_rotary_pos_emb / rotate_half, layers/positional_embeddings.py:71-87, applied to one of {q, k} inside the packed QKV
+ * projection output (layers/transformer.py:488-523): head h of row t starts at x + t*row_stride + h*head_stride.
+ * cos/sin: fp32 [max_pos, head_dim/2] (RotaryEmbedding cache, positional_embeddings.py:38-52); positions int64 [rows].
+ * backward != 0 applies the transposed rotation (gradient). head_dim % 16 == 0. */
+int fsb_rope_inplace(void* x, const float* cos_table, const float* sin_table, const int64_t* positions, int64_t rows,
+                     int nheads, int head_dim, int64_t row_stride, int64_t head_stride, int64_t max_pos, int backward,
+                     fsb_stream_t stream);
+
+/* ---- gated / plain activations ------------------------------------------------------------------------------
+ * act: 0 SiLU (LLaMAParallelMLP.forward layers/transformer.py:620-623: silu(w1 x) * w3 x), 1 tanh-GeLU (gelu_new /
+ * bias_gelu layers/activations.py:60-94; MT5DenseGatedActDense), 2 erf-GeLU (activations.py:98-117; BERT).
+ * glu: out[t,c] = act(gate[t,c]) * up[t,c] with independent row strides (gate|up are column halves of one GEMM output). */
+int fsb_glu_fwd(int act, const void* gate, const void* up, void* out, int64_t rows, int64_t cols, int64_t ld_gate,
+                int64_t ld_up, int64_t ld_out, fsb_stream_t stream);
+int fsb_glu_bwd(int act, const void* dout, const void* gate, const void* up, void* dgate, void* dup, int64_t rows,
+                int64_t cols, int64_t ld_dout, int64_t ld_gate, int64_t ld_up, int64_t ld_dgate, int64_t ld_dup,
+                fsb_stream_t stream);
+int fsb_act_fwd(int act, const void* x, void* y, int64_t n, fsb_stream_t stream);
+int fsb_act_bwd(int act, const void* dy, const void* x, void* dx, int64_t n, fsb_stream_t stream);
+int fsb_add(const void* a, const void* b, void* out, int64_t n, fsb_stream_t stream);            /* bf16, n % 8 == 0 */
+/* acc (fp32) = (overwrite ? 0 : acc) + scale * x (bf16): ZeRO-2 per-micro-step gradient accumulation into the fp32 shard */
+int fsb_accumulate(float* acc, const void* x, int64_t n, float scale, int overwrite, fsb_stream_t stream);
+/* out[c] (+)= sum_r x[r,c]  (bias gradients; learned-position gradient as [B, S*h] column sum); deterministic */
+size_t fsb_colsum_workspace_bytes(int64_t rows, int64_t cols);
+int fsb_colsum(const void* x, int64_t rows, int64_t cols, int64_t ld, void* out, int out_dtype, int accumulate,
+               void* workspace, size_t workspace_bytes, fsb_stream_t stream);
+
+/* ---- embedding ----------------------------------------------------------------------------------------------
+ * VocabParallelEmbedding.forward fengshen/models/megatron/mpu/layers.py:104-130 (TP = 1): out[t] = W[ids[t]]
+ * (+ P[pos[t]] learned positions, pos == NULL -> t % seq_len; + T[token_type[t]]) — HF BertEmbeddings / GPT-2 wte + wpe.
+ * Backward scatter-adds bf16 rows into dW (ids == NULL -> row t % idx_mod). */
+int fsb_embedding_fwd(const int64_t* ids, const int64_t* pos, const int64_t* token_type, const void* W, const void* P,
+                      const void* T, void* out, int64_t rows, int64_t cols, int64_t seq_len, fsb_stream_t stream);
+int fsb_embedding_bwd(const int64_t* ids, const void* dout, void* dW, int64_t rows, int64_t cols, int64_t idx_mod,
+                      fsb_stream_t stream);
+
+/* ---- fused softmax cross-entropy, forward + backward ----------------------------------------------------------
+ * torch.nn.CrossEntropyLoss()(shift_logits, shift_labels), fengshen/models/llama/modeling_llama.py:334-339: mean NLL over
+ * labels != ignore_index. Row t = (b, s) uses labels[t + shift] and is ignored when s + shift >= seq_len (the
+ * shift-by-one without the `.contiguous()` copy of :336). logits bf16 [rows, vocab] (row stride ld); dlogits (may alias
+ * logits, may be NULL) receives (softmax - onehot) * grad_scale / n_valid. row_loss fp32 [rows], loss fp32 [1],
+ * n_valid int32 [1] are device outputs (token-id side is bit-exact: n_valid and the one-hot index). */
+int fsb_softmax_xent_fwd_bwd(const void* logits, const int64_t* labels, void* dlogits, float* row_loss, float* loss,
+                             int* n_valid, int64_t rows, int64_t vocab, int64_t ld, int64_t seq_len, int shift,
+                             int ignore_index, float grad_scale, fsb_stream_t stream);
+
+/* ---- flat-shard AdamW, gradient norm, clip ------------------------------------------------------------------
+ * deepspeed.ops.adam.FusedAdam(adam_w_mode=True) as selected at fengshen/models/model_utils.py:69-72, in
+ * torch.optim.AdamW's operation order, on the rank's flat fp32 shard {master, exp_avg, exp_avg_sq}; grad bf16 or fp32;
+ * param16 (bf16, may be NULL) receives the updated parameters. grad_scale: optional DEVICE scalar multiplied into the
+ * gradient (clip coefficient). n % 4 == 0. fsb_sumsq / fsb_clip_coef give torch.nn.utils.clip_grad_norm_ semantics. */
+int fsb_adamw_flat(float* master, float* exp_avg, float* exp_avg_sq, const void* grad, int grad_dtype, void* param16,
+                   int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                   const float* grad_scale, fsb_stream_t stream);
+size_t fsb_sumsq_workspace_bytes(void);
+int fsb_sumsq(const void* x, int dtype, int64_t n, float* out, int accumulate, void* workspace, size_t workspace_bytes,
+              fsb_stream_t stream);
+int fsb_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, fsb_stream_t stream);
+
 /* ---- fused scaled-dot-product attention (tcgen05, flash-style online softmax) ------------------------------
  * Replaces ParallelSelfAttention.flash_attention (fengshen/models/megatron/layers/transformer.py:410-456; 3P
  * flash_attn_cuda.fwd/bwd, layers/flash_attention.py:31-47,81-101) and the legacy baddbmm -> FusedScaleMaskSoftmax ->
