@@ -19,7 +19,15 @@ namespace fsb {
 int make_attn_tmap(CUtensorMap* tm, const void* base, int64_t row_stride, int64_t width, int64_t seq, int64_t batch,
                    int box_rows);
 
-constexpr int AB_THREADS = 192;  // warps 0-3: math warpgroup; warp 4: TMA; warp 5: MMA + TMEM owner
+constexpr int AB_THREADS = 320;  // warps 0-7: math (2 threads per row, 32 columns each); warp 8: TMA; warp 9: MMA + TMEM owner
+constexpr int AB_MATH = 256;
+constexpr int AB_W_TMA = 8, AB_W_MMA = 9;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 constexpr int AB_BM = 128;       // rows owned by the CTA (queries for dQ, keys for dKV) == TMEM lanes
 constexpr int AB_BN = 64;        // streamed tile (keys for dQ, queries for dKV)
 
@@ -71,7 +79,7 @@ struct AttBwdSmem {
   static constexpr int BIG_BYTES = AB_BM * D * 2;    // a resident 128-row tile
   static constexpr int SML_BYTES = AB_BN * D * 2;    // a streamed 64-row tile
   static constexpr int T_BYTES = AB_BM * AB_BN * 2;  // bf16 [128 x 64] P / dS tile
-  static constexpr int STAGES = 2;
+  static constexpr int STAGES = (D == 64) ? 3 : 2;
   static constexpr int OFF_BIG0 = 0;                       // dQ: Q     | dKV: K
   static constexpr int OFF_BIG1 = OFF_BIG0 + BIG_BYTES;    // dQ: dO    | dKV: V
   static constexpr int OFF_SML0 = OFF_BIG1 + BIG_BYTES;    // dQ: K_j   | dKV: Q_i   (STAGES)
@@ -116,21 +124,21 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int n_all = (p.seq_kv + AB_BN - 1) / AB_BN;
   const int n_steps = p.causal ? min(n_all, (min(q0 + AB_BM, p.seq_q) + AB_BN - 1) / AB_BN) : n_all;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == AB_W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(big_full, 1);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&sml_full[i], 1); mbar_init(&sml_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&t_ready[i], AB_BM); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&t_ready[i], AB_MATH); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  if (warp == AB_W_MMA) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 4) {
+  if (warp == AB_W_TMA) {
     if (lane == 0) {
       const int qc = head * p.q_head_stride, dc = head * p.do_head_stride;
       const int kc = head * p.k_head_stride, vc = head * p.v_head_stride;
@@ -154,7 +162,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (++st == STAGES) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == AB_W_MMA) {
     if (lane == 0) {
       auto issue_s_dp = [&](int buf, int st) {
         const uint32_t sq = smem_u32(smem + S::OFF_BIG0), sdo = smem_u32(smem + S::OFF_BIG1);
@@ -204,8 +212,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       umma_commit(done);
     }
   } else {
-    // ---- math warpgroup: one thread per query row
-    const int quad = warp & 3;
+    // ---- math warps: two threads per query row (warp w and w+4 share a TMEM lane quadrant, 32 key columns each)
+    const int quad = warp & 3, half = warp >> 2;
     const int r_in = quad * 32 + lane;
     const int q_row = q0 + r_in;
     const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16);
@@ -219,51 +227,51 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int buf = j & 1;
       mbar_wait(&s_full[buf], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t s0[32], s1[32];
-      tmem_ld32(t_lane + TM_S + buf * 128, s0);
-      tmem_ld32(t_lane + TM_S + buf * 128 + 32, s1);
+      uint32_t s[32], d[32];
+      tmem_ld32(t_lane + TM_S + buf * 128 + half * 32, s);
+      tmem_ld32(t_lane + TM_S + buf * 128 + 64 + half * 32, d);
       tmem_ld_wait();
-      const int kv0 = j * AB_BN;
-      const bool need_mask = (p.causal && kv0 + AB_BN - 1 > q0) || (kv0 + AB_BN > p.seq_kv) || mrow;
+      const int c0 = j * AB_BN + half * 32;
+      const bool need_mask = (p.causal && j * AB_BN + AB_BN - 1 > q0) || (j * AB_BN + AB_BN > p.seq_kv) || mrow;
+      uint32_t pk[16];
+      if (!need_mask) {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float pv = exp2f(__uint_as_float(c < 32 ? s0[c & 31] : s1[c & 31]) * p.scale_log2 - lse);
-        if (need_mask) {
-          const int col = kv0 + c;
-          bool keep = col < p.seq_kv && !(p.causal && col > q_row);
-          if (keep && mrow) keep = mrow[col] != 0;
-          pv = keep ? pv : 0.f;
+        for (int c = 0; c < 32; c += 2) {
+          const float p0 = ex2_approx(__uint_as_float(s[c]) * p.scale_log2 - lse);
+          const float p1 = ex2_approx(__uint_as_float(s[c + 1]) * p.scale_log2 - lse);
+          pk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(d[c]) - delta), p1 * (__uint_as_float(d[c + 1]) - delta));
         }
-        if (c < 32) s0[c & 31] = __float_as_uint(pv); else s1[c & 31] = __float_as_uint(pv);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float pv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = c0 + c + e;
+            bool keep = col < p.seq_kv && !(p.causal && col > q_row);
+            if (keep && mrow) keep = mrow[col] != 0;
+            pv[e] = keep ? ex2_approx(__uint_as_float(s[c + e]) * p.scale_log2 - lse) : 0.f;
+          }
+          pk[c >> 1] = pack_bf16x2(pv[0] * (__uint_as_float(d[c]) - delta), pv[1] * (__uint_as_float(d[c + 1]) - delta));
+        }
       }
       uint8_t* sds = smem + S::OFF_T0 + buf * S::T_BYTES + r_in * 128;
 #pragma unroll
-      for (int hc = 0; hc < 2; ++hc) {
-        uint32_t d[32];
-        tmem_ld32(t_lane + TM_S + buf * 128 + 64 + hc * 32, d);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          const float p0 = __uint_as_float(hc == 0 ? s0[c] : s1[c]), p1 = __uint_as_float(hc == 0 ? s0[c + 1] : s1[c + 1]);
-          pk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(d[c]) - delta), p1 * (__uint_as_float(d[c + 1]) - delta));
-        }
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch)
-          *reinterpret_cast<uint4*>(sds + (((hc * 4 + ch) ^ sw) << 4)) =
-              make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-      }
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(sds + (((half * 4 + ch) ^ sw) << 4)) =
+            make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&t_ready[buf]);
     }
-    // ---- epilogue
+    // ---- epilogue: the two threads of a row take alternate 32-column chunks of dQ
     mbar_wait(done, 0);
     tc_fence_after();
     if (n_steps > 0) {
       __nv_bfloat16* dqp = p.dq + (int64_t(b) * p.seq_q + q_row) * p.dq_row_stride + int64_t(head) * p.dq_head_stride;
 #pragma unroll
-      for (int ch = 0; ch < D / 32; ++ch) {
+      for (int cc = 0; cc < D / 64; ++cc) {
+        const int ch = cc * 2 + half;
         uint32_t t[32];
         tmem_ld32(t_lane + TM_DQ + ch * 32, t);
         tmem_ld_wait();
@@ -281,7 +289,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == AB_W_MMA) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
@@ -322,21 +330,21 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   const int i_start = p.causal ? min(n_q, kv0 / AB_BN) : 0;
   const int n_steps = n_q - i_start;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == AB_W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(big_full, 1);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&sml_full[i], 1); mbar_init(&sml_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&t_ready[i], AB_BM); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&t_ready[i], AB_MATH); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  if (warp == AB_W_MMA) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 4) {
+  if (warp == AB_W_TMA) {
     if (lane == 0) {
       const int qc = head * p.q_head_stride, dc = head * p.do_head_stride;
       const int kc = head * p.k_head_stride, vc = head * p.v_head_stride;
@@ -360,7 +368,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         if (++st == STAGES) { st = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == AB_W_MMA) {
     if (lane == 0) {
       auto issue_st_dpt = [&](int buf, int st) {
         const uint32_t sk = smem_u32(smem + S::OFF_BIG0), sv = smem_u32(smem + S::OFF_BIG1);
@@ -416,8 +424,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       umma_commit(done);
     }
   } else {
-    // ---- math warpgroup: one thread per KEY row
-    const int quad = warp & 3;
+    // ---- math warps: two threads per KEY row (32 query columns each)
+    const int quad = warp & 3, half = warp >> 2;
     const int r_in = quad * 32 + lane;
     const int kv_row = kv0 + r_in;
     const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16);
@@ -425,61 +433,58 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     const bool store_ok = row_ok;
     if (row_ok && p.kv_mask) row_ok = p.kv_mask[int64_t(b) * p.seq_kv + kv_row] != 0;
     const int sw = r_in & 7;
+    const int tid = threadIdx.x;  // 0..255 inside the math group
     const int64_t stat_base = (int64_t(b) * p.nheads + head) * p.seq_q;
     for (int i = 0; i < n_steps; ++i) {
       const int buf = i & 1;
       const int qt0 = (i_start + i) * AB_BN;
-      {  // stage lse / delta of this query tile (thread t<64: lse, t>=64: delta)
-        const int c = r_in & 63;
+      if (tid < 128) {  // stage lse / delta of this query tile (tid < 64: lse, 64..127: delta)
+        const int c = tid & 63;
         const int qi = qt0 + c;
         float val;
-        if (r_in < 64) val = qi < p.seq_q ? p.lse[stat_base + qi] : INFINITY;
+        if (tid < 64) val = qi < p.seq_q ? p.lse[stat_base + qi] : INFINITY;
         else val = qi < p.seq_q ? p.delta[stat_base + qi] : 0.f;
-        stats[buf * 128 + (r_in < 64 ? 0 : 64) + c] = val;
+        stats[buf * 128 + (tid < 64 ? 0 : 64) + c] = val;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&s_full[buf], (i >> 1) & 1);
       tc_fence_after();
-      const float* lse_s = stats + buf * 128;
+      const float* lse_s = stats + buf * 128 + half * 32;
       const float* del_s = lse_s + 64;
+      uint32_t s[32], d[32];
+      tmem_ld32(t_lane + TM_S + buf * 128 + half * 32, s);
+      tmem_ld32(t_lane + TM_S + buf * 128 + 64 + half * 32, d);
+      tmem_ld_wait();
+      const bool need_causal = p.causal && (qt0 < kv0 + AB_BM - 1);
+      uint32_t pp[16], pd[16];
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        float pv[2], dv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float x = ex2_approx(__uint_as_float(s[c + e]) * p.scale_log2 - lse_s[c + e]);
+          const bool keep = row_ok && !(need_causal && (qt0 + half * 32 + c + e) < kv_row);
+          x = keep ? x : 0.f;
+          pv[e] = x;
+          dv[e] = x * (__uint_as_float(d[c + e]) - del_s[c + e]);
+        }
+        pp[c >> 1] = pack_bf16x2(pv[0], pv[1]);
+        pd[c >> 1] = pack_bf16x2(dv[0], dv[1]);
+      }
       uint8_t* spt = smem + S::OFF_T0 + buf * S::T_BYTES + r_in * 128;
       uint8_t* sdst = smem + S::OFF_T1 + buf * S::T_BYTES + r_in * 128;
-      const bool need_causal = p.causal && (qt0 < kv0 + AB_BM - 1);
 #pragma unroll
-      for (int hc = 0; hc < 2; ++hc) {
-        uint32_t s[32], d[32];
-        tmem_ld32(t_lane + TM_S + buf * 128 + hc * 32, s);
-        tmem_ld32(t_lane + TM_S + buf * 128 + 64 + hc * 32, d);
-        tmem_ld_wait();
-        uint32_t pp[16], pd[16];
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float pv[2], dv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int cc = hc * 32 + c + e;
-            float x = exp2f(__uint_as_float(s[c + e]) * p.scale_log2 - lse_s[cc]);
-            const bool keep = row_ok && !(need_causal && (qt0 + cc) < kv_row);
-            x = keep ? x : 0.f;
-            pv[e] = x;
-            dv[e] = x * (__uint_as_float(d[c + e]) - del_s[cc]);
-          }
-          pp[c >> 1] = pack_bf16x2(pv[0], pv[1]);
-          pd[c >> 1] = pack_bf16x2(dv[0], dv[1]);
-        }
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          *reinterpret_cast<uint4*>(spt + (((hc * 4 + ch) ^ sw) << 4)) =
-              make_uint4(pp[ch * 4], pp[ch * 4 + 1], pp[ch * 4 + 2], pp[ch * 4 + 3]);
-          *reinterpret_cast<uint4*>(sdst + (((hc * 4 + ch) ^ sw) << 4)) =
-              make_uint4(pd[ch * 4], pd[ch * 4 + 1], pd[ch * 4 + 2], pd[ch * 4 + 3]);
-        }
+      for (int ch = 0; ch < 4; ++ch) {
+        *reinterpret_cast<uint4*>(spt + (((half * 4 + ch) ^ sw) << 4)) =
+            make_uint4(pp[ch * 4], pp[ch * 4 + 1], pp[ch * 4 + 2], pp[ch * 4 + 3]);
+        *reinterpret_cast<uint4*>(sdst + (((half * 4 + ch) ^ sw) << 4)) =
+            make_uint4(pd[ch * 4], pd[ch * 4 + 1], pd[ch * 4 + 2], pd[ch * 4 + 3]);
       }
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(&t_ready[buf]);
     }
-    // ---- epilogue: dV, dK
+    // ---- epilogue: dV, dK; the two threads of a row take alternate 32-column chunks
     mbar_wait(done, 0);
     tc_fence_after();
     __nv_bfloat16* dvp = p.dv + (int64_t(b) * p.seq_kv + kv_row) * p.dv_row_stride + int64_t(head) * p.dv_head_stride;
@@ -487,7 +492,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
 #pragma unroll
-      for (int ch = 0; ch < D / 32; ++ch) {
+      for (int cc = 0; cc < D / 64; ++cc) {
+        const int ch = cc * 2 + half;
         uint32_t t[32];
         if (n_steps > 0) {
           tmem_ld32(t_lane + (which == 0 ? TM_DV : TM_DK) + ch * 32, t);
@@ -512,7 +518,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == AB_W_MMA) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }

@@ -50,6 +50,11 @@ struct AttFwdParams {
   float scale_log2;  // softmax scale * log2(e)
 };
 
+__device__ __forceinline__ float ex2_approx_f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <int kRegs>
 __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 template <int kRegs>
@@ -230,27 +235,34 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int kv0 = j * ATT_BKV;
       const bool need_mask = (p.causal && kv0 + ATT_BKV - 1 > q0 + slot * ATT_BQ) || (kv0 + ATT_BKV > p.seq_kv) || mrow;
       float mx = -INFINITY;
+      if (!need_mask) {
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        float s = __uint_as_float(c < 32 ? r0[c & 31] : r1[c & 31]) * p.scale_log2;
-        if (need_mask) {
+        for (int c = 0; c < 32; ++c) {
+          const float a = __uint_as_float(r0[c]) * p.scale_log2, bq = __uint_as_float(r1[c]) * p.scale_log2;
+          r0[c] = __float_as_uint(a); r1[c] = __float_as_uint(bq);
+          mx = fmaxf(mx, fmaxf(a, bq));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          float s = __uint_as_float(c < 32 ? r0[c & 31] : r1[c & 31]) * p.scale_log2;
           const int col = kv0 + c;
           bool keep = col < p.seq_kv && !(p.causal && col > q_row);
           if (keep && mrow) keep = mrow[col] != 0;
           s = keep ? s : -INFINITY;
+          if (c < 32) r0[c & 31] = __float_as_uint(s); else r1[c & 31] = __float_as_uint(s);
+          mx = fmaxf(mx, s);
         }
-        if (c < 32) r0[c & 31] = __float_as_uint(s); else r1[c & 31] = __float_as_uint(s);
-        mx = fmaxf(mx, s);
       }
       const float m_new = fmaxf(m_run, mx);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m_run - m_use);  // m_run == -inf -> 0
+      const float alpha = ex2_approx_f(m_run - m_use);  // m_run == -inf -> 0
       float sum = 0.f;
       uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
-        const float a = exp2f(__uint_as_float(c < 32 ? r0[c & 31] : r1[c & 31]) - m_use);
-        const float bb = exp2f(__uint_as_float(c + 1 < 32 ? r0[(c + 1) & 31] : r1[(c + 1) & 31]) - m_use);
+        const float a = ex2_approx_f(__uint_as_float(c < 32 ? r0[c & 31] : r1[c & 31]) - m_use);
+        const float bb = ex2_approx_f(__uint_as_float(c + 1 < 32 ? r0[(c + 1) & 31] : r1[(c + 1) & 31]) - m_use);
         pk[c >> 1] = pack_bf16x2(a, bb);
         // sum what the tensor core will actually see (bf16-rounded), keeps rows normalised
         sum += bf16lo(pk[c >> 1]) + bf16hi(pk[c >> 1]);

@@ -167,6 +167,20 @@ __global__ void __launch_bounds__(256) add_kernel(const uint4* __restrict__ a, c
   }
 }
 
+// x *= *scale (device scalar); exits without touching memory when *scale == 1 (the usual upstream gradient of a loss)
+__global__ void __launch_bounds__(256) scale_inplace_kernel(uint4* __restrict__ x, int64_t nvec,
+                                                            const float* __restrict__ scale) {
+  const float s = *scale;
+  if (s == 1.0f) return;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nvec; i += int64_t(gridDim.x) * blockDim.x) {
+    float f[8];
+    unpack8(x[i], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= s;
+    x[i] = pack8(f);
+  }
+}
+
 // acc (fp32) += scale * x (bf16)   — gradient accumulation into the fp32 shard (ZeRO-2 per-micro-step reduce)
 __global__ void __launch_bounds__(256) accumulate_kernel(float* __restrict__ acc, const uint2* __restrict__ x,
                                                          int64_t nvec, float scale, int overwrite) {
@@ -358,6 +372,12 @@ extern "C" int fsb_act_bwd(int act, const void* dy, const void* x, void* dx, int
 extern "C" int fsb_add(const void* a, const void* b, void* out, int64_t n, fsb_stream_t st) {
   FSB_REQUIRE(a && b && out && n > 0 && n % 8 == 0 && aligned16(a) && aligned16(b) && aligned16(out), "add: bad args");
   add_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)st>>>((const uint4*)a, (const uint4*)b, (uint4*)out, n / 8);
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+extern "C" int fsb_scale_inplace(void* x, int64_t n, const float* scale_dev, fsb_stream_t st) {
+  FSB_REQUIRE(x && scale_dev && n > 0 && n % 8 == 0 && aligned16(x), "scale_inplace: bad args (n %% 8 == 0, aligned)");
+  scale_inplace_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)st>>>((uint4*)x, n / 8, scale_dev);
   FSB_CUDA_LAUNCH_CHECK();
   return FSB_OK;
 }

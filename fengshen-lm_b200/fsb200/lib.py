@@ -47,6 +47,7 @@ SIGNATURES = {
     "fsb_act_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "fsb_add": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "fsb_accumulate": (c_int, [c_void_p, c_void_p, c_i64, c_f32, c_int, c_void_p]),
+    "fsb_scale_inplace": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
     "fsb_colsum_workspace_bytes": (c_size, [c_i64, c_i64]),
     "fsb_colsum": (c_int, [c_void_p, c_i64, c_i64, c_i64, c_void_p, c_int, c_int, c_void_p, c_size, c_void_p]),
     "fsb_embedding_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64,

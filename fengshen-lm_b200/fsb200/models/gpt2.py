@@ -178,7 +178,7 @@ class GPT2LMHeadModel(nn.Module):
         tr = self.transformer
         scale = 1.0 / math.sqrt(hn)
         if gloss is not None:
-            dlogits.mul_(gloss.to(dlogits.dtype))
+            ops.scale_inplace(dlogits, gloss)  # upstream scalar; the kernel exits immediately when it is 1.0
         wte = tr.wte.weight
         dhf = ops.gemm(L.GEMM_NN, dlogits, wte.data)
         ops.gemm(L.GEMM_TN, dlogits, hf, out=wte.main_grad, accumulate=acc)   # tied head: written first, embedding adds later

@@ -211,7 +211,7 @@ class LlamaForCausalLM(nn.Module):
         T = B * S
         acc = self.accumulate_grads
         if gloss is not None:
-            dlogits.mul_(gloss.to(dlogits.dtype))  # upstream scalar (normally 1.0); host plumbing, off the hot path
+            ops.scale_inplace(dlogits, gloss)  # upstream scalar; the kernel exits immediately when it is 1.0
         W_out = self.embed_out.final_linear.weight
         dhf = ops.gemm(L.GEMM_NN, dlogits, W_out.data)
         ops.gemm(L.GEMM_TN, dlogits, hf, out=W_out.main_grad, accumulate=acc)

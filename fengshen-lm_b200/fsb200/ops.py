@@ -207,6 +207,13 @@ def accumulate(acc32, x16, scale=1.0, overwrite=False):
     L.call("fsb_accumulate", _p(acc32), _p(x16), acc32.numel(), float(scale), int(bool(overwrite)), _stream())
 
 
+def scale_inplace(x16, scale_dev):
+    """x16 (bf16, contiguous) *= scale_dev (0-d fp32 CUDA tensor); free when the scalar is 1."""
+    if scale_dev.dtype != torch.float32 or not scale_dev.is_cuda:
+        scale_dev = scale_dev.to(device=x16.device, dtype=torch.float32)
+    L.call("fsb_scale_inplace", _p(x16), x16.numel(), _p(scale_dev), _stream())
+
+
 def colsum(x, out, accumulate=False):
     """out[c] (+)= sum_r x[r, c]; x bf16 [rows, cols] (unit inner stride); out bf16 or fp32 [cols]."""
     rows, cols, ld = _rows2d(x, "x")

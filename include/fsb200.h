@@ -113,6 +113,8 @@ int fsb_glu_bwd(int act, const void* dout, const void* gate, const void* up, voi
 int fsb_act_fwd(int act, const void* x, void* y, int64_t n, fsb_stream_t stream);
 int fsb_act_bwd(int act, const void* dy, const void* x, void* dx, int64_t n, fsb_stream_t stream);
 int fsb_add(const void* a, const void* b, void* out, int64_t n, fsb_stream_t stream);            /* bf16, n % 8 == 0 */
+/* x (bf16, n % 8 == 0) *= *scale_dev; a no-op launch when the device scalar is 1 (upstream gradient of the loss) */
+int fsb_scale_inplace(void* x, int64_t n, const float* scale_dev, fsb_stream_t stream);
 /* acc (fp32) = (overwrite ? 0 : acc) + scale * x (bf16): ZeRO-2 per-micro-step gradient accumulation into the fp32 shard */
 int fsb_accumulate(float* acc, const void* x, int64_t n, float scale, int overwrite, fsb_stream_t stream);
 /* out[c] (+)= sum_r x[r,c]  (bias gradients; learned-position gradient as [B, S*h] column sum); deterministic */
