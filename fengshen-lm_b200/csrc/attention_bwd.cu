@@ -74,19 +74,19 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 }
 
 // ------------------------------------------------------------------------------------------------ shared layout
-template <int D>
+template <int D, int kStages, int kTBufs>
 struct AttBwdSmem {
   static constexpr int BIG_BYTES = AB_BM * D * 2;    // a resident 128-row tile
   static constexpr int SML_BYTES = AB_BN * D * 2;    // a streamed 64-row tile
   static constexpr int T_BYTES = AB_BM * AB_BN * 2;  // bf16 [128 x 64] P / dS tile
-  static constexpr int STAGES = (D == 64) ? 3 : 2;
+  static constexpr int STAGES = kStages;  // streamed-tile ring depth: must cover the TMA round trip (~2 us)
   static constexpr int OFF_BIG0 = 0;                       // dQ: Q     | dKV: K
   static constexpr int OFF_BIG1 = OFF_BIG0 + BIG_BYTES;    // dQ: dO    | dKV: V
   static constexpr int OFF_SML0 = OFF_BIG1 + BIG_BYTES;    // dQ: K_j   | dKV: Q_i   (STAGES)
   static constexpr int OFF_SML1 = OFF_SML0 + STAGES * SML_BYTES;  // dQ: V_j | dKV: dO_i
   static constexpr int OFF_T0 = OFF_SML1 + STAGES * SML_BYTES;    // dQ: dS[2] | dKV: P^T[2]
   static constexpr int OFF_T1 = OFF_T0 + 2 * T_BYTES;             //           | dKV: dS^T[2]
-  static constexpr int OFF_STATS = OFF_T1 + 2 * T_BYTES;          // float [2][2][64] (dKV only)
+  static constexpr int OFF_STATS = OFF_T0 + kTBufs * T_BYTES;     // float [2][2][64] (dKV only)
   static constexpr int OFF_BAR = OFF_STATS + 2 * 2 * 64 * 4;
   static constexpr int NBAR = 1 + 2 * STAGES + 2 + 2 + 1;  // big_full, sml_full[S], sml_empty[S], s_full[2], t_ready[2], done
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const AttBwdParams p) {
-  using S = AttBwdSmem<D>;
+  using S = AttBwdSmem<D, (D == 64 ? 6 : 4), 2>;
   constexpr int STAGES = S::STAGES;
   constexpr int TMEM_COLS = 512;
   constexpr int TM_S = 0;     // S[buf] at buf*128, dP[buf] at buf*128 + 64
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                     const AttBwdParams p) {
-  using S = AttBwdSmem<D>;
+  using S = AttBwdSmem<D, (D == 64 ? 6 : 3), 4>;
   constexpr int STAGES = S::STAGES;
   constexpr int TMEM_COLS = 512;
   constexpr int TM_S = 0;             // S^T[buf] at buf*128, dP^T[buf] at buf*128 + 64
@@ -528,13 +528,14 @@ template <int D>
 static int launch_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
                            int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, int64_t do_rs, int64_t o_hs,
                            float* delta, AttBwdParams& p, cudaStream_t st) {
-  using S = AttBwdSmem<D>;
+  using SQ = AttBwdSmem<D, (D == 64 ? 6 : 4), 2>;
+  using SK = AttBwdSmem<D, (D == 64 ? 6 : 3), 4>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
-    cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ::TOTAL);
+    cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK::TOTAL);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
-      set_error("sdpa_bwd: cudaFuncSetAttribute(%d) failed", S::TOTAL);
+      set_error("sdpa_bwd: cudaFuncSetAttribute(%d / %d) failed", SQ::TOTAL, SK::TOTAL);
       return FSB_ERR_CUDA;
     }
     configured = true;
@@ -563,13 +564,13 @@ static int launch_attn_bwd(const void* q, const void* k, const void* v, const vo
   // 2. dQ
   {
     dim3 grid((p.seq_q + AB_BM - 1) / AB_BM, p.nheads, p.batch);
-    attn_bwd_dq_kernel<D><<<grid, AB_THREADS, S::TOTAL, st>>>(tq128, tdo128, tk64, tv64, p);
+    attn_bwd_dq_kernel<D><<<grid, AB_THREADS, SQ::TOTAL, st>>>(tq128, tdo128, tk64, tv64, p);
     FSB_CUDA_LAUNCH_CHECK();
   }
   // 3. dK, dV
   {
     dim3 grid((p.seq_kv + AB_BM - 1) / AB_BM, p.nheads, p.batch);
-    attn_bwd_dkv_kernel<D><<<grid, AB_THREADS, S::TOTAL, st>>>(tk128, tv128, tq64, tdo64, p);
+    attn_bwd_dkv_kernel<D><<<grid, AB_THREADS, SK::TOTAL, st>>>(tk128, tv128, tq64, tdo64, p);
     FSB_CUDA_LAUNCH_CHECK();
   }
   return FSB_OK;

@@ -24,7 +24,7 @@ constexpr int ATT_THREADS = 384;
 
 template <int D>
 struct AttFwdSmem {
-  static constexpr int STAGES = (D == 128) ? 3 : 4;
+  static constexpr int STAGES = (D == 128) ? 4 : 8;  // K/V ring depth: must cover the TMA round trip
   static constexpr int Q_BYTES = ATT_BQ * D * 2;       // per slot
   static constexpr int KV_BYTES = ATT_BKV * D * 2;     // per tensor per stage
   static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2; // per slot
