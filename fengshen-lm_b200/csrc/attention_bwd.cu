@@ -42,6 +42,14 @@ struct AttBwdParams {
   float scale, scale_log2;
 };
 
+// Optional cycle trace of one CTA (development aid; compiled in only with -DFSB_ATTN_TRACE)
+#ifdef FSB_ATTN_TRACE
+__device__ long long g_attn_trace[2][64][8];
+#define TRACE(role, step, k) do { if (trace_on && (step) < 64) g_attn_trace[role][step][k] = clock64(); } while (0)
+#else
+#define TRACE(role, step, k) do { } while (0)
+#endif
+
 // ------------------------------------------------------------------------------------------------ delta preprocess
 template <int D>
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
@@ -123,6 +131,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const int q0 = tile * AB_BM;
   const int n_all = (p.seq_kv + AB_BN - 1) / AB_BN;
   const int n_steps = p.causal ? min(n_all, (min(q0 + AB_BM, p.seq_q) + AB_BN - 1) / AB_BN) : n_all;
+#ifdef FSB_ATTN_TRACE
+  const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0 &&
+                        (warp == 0 || warp == AB_W_MMA);
+#endif
 
   if (warp == AB_W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -163,54 +175,65 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
   } else if (warp == AB_W_MMA) {
-    if (lane == 0) {
-      auto issue_s_dp = [&](int buf, int st) {
-        const uint32_t sq = smem_u32(smem + S::OFF_BIG0), sdo = smem_u32(smem + S::OFF_BIG1);
-        const uint32_t sk = smem_u32(smem + S::OFF_SML0 + st * S::SML_BYTES);
-        const uint32_t sv = smem_u32(smem + S::OFF_SML1 + st * S::SML_BYTES);
+    // Warp-uniform loop; one elected lane issues. Descriptors are base constants plus compile-time offsets (>> 4).
+    const uint64_t dsc_q = make_smem_desc_sw128(smem_u32(smem + S::OFF_BIG0), 0, 1024);
+    const uint64_t dsc_do = make_smem_desc_sw128(smem_u32(smem + S::OFF_BIG1), 0, 1024);
+    const uint64_t dsc_k = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML0), 0, 1024);          // K-major view (S)
+    const uint64_t dsc_v = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML1), 0, 1024);
+    const uint64_t dsc_kmn = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML0), AB_BN * 128, 1024);  // MN-major view (dQ)
+    const uint64_t dsc_ds = make_smem_desc_sw128(smem_u32(smem + S::OFF_T0), 0, 1024);
+    auto issue_s_dp = [&](int buf, int st) {
+      if (elect_one()) {
+        const uint64_t sto = uint64_t(st) * (S::SML_BYTES >> 4);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t oa = (kk / 4) * (AB_BM * 128) + (kk % 4) * 32, ob = (kk / 4) * (AB_BN * 128) + (kk % 4) * 32;
-          umma_bf16(tmem_base + TM_S + buf * 128, make_smem_desc_sw128(sq + oa, 0, 1024),
-                    make_smem_desc_sw128(sk + ob, 0, 1024), IDESC_S, kk != 0);
+          const uint32_t oa = ((kk / 4) * (AB_BM * 128) + (kk % 4) * 32) >> 4, ob = ((kk / 4) * (AB_BN * 128) + (kk % 4) * 32) >> 4;
+          umma_bf16(tmem_base + TM_S + buf * 128, dsc_q + oa, dsc_k + sto + ob, IDESC_S, kk != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t oa = (kk / 4) * (AB_BM * 128) + (kk % 4) * 32, ob = (kk / 4) * (AB_BN * 128) + (kk % 4) * 32;
-          umma_bf16(tmem_base + TM_S + buf * 128 + 64, make_smem_desc_sw128(sdo + oa, 0, 1024),
-                    make_smem_desc_sw128(sv + ob, 0, 1024), IDESC_S, kk != 0);
+          const uint32_t oa = ((kk / 4) * (AB_BM * 128) + (kk % 4) * 32) >> 4, ob = ((kk / 4) * (AB_BN * 128) + (kk % 4) * 32) >> 4;
+          umma_bf16(tmem_base + TM_S + buf * 128 + 64, dsc_do + oa, dsc_v + sto + ob, IDESC_S, kk != 0);
         }
-      };
-      mbar_wait(big_full, 0);
-      if (n_steps > 0) {
-        mbar_wait(&sml_full[0], 0);
-        tc_fence_after();
-        issue_s_dp(0, 0);
-        umma_commit(&s_full[0]);
+        umma_commit(&s_full[buf]);
       }
-      int st = 0; uint32_t ph = 0;
-      for (int j = 0; j < n_steps; ++j) {
-        int st1 = st + 1; uint32_t ph1 = ph;
-        if (st1 == STAGES) { st1 = 0; ph1 ^= 1; }
-        if (j + 1 < n_steps) {
-          mbar_wait(&sml_full[st1], ph1);
-          tc_fence_after();
-          issue_s_dp((j + 1) & 1, st1);
-          umma_commit(&s_full[(j + 1) & 1]);
-        }
-        mbar_wait(&t_ready[j & 1], (j >> 1) & 1);
+      __syncwarp();
+    };
+    mbar_wait(big_full, 0);
+    if (n_steps > 0) {
+      mbar_wait(&sml_full[0], 0);
+      tc_fence_after();
+      issue_s_dp(0, 0);
+    }
+    int st = 0; uint32_t ph = 0;
+    for (int j = 0; j < n_steps; ++j) {
+      int st1 = st + 1; uint32_t ph1 = ph;
+      if (st1 == STAGES) { st1 = 0; ph1 ^= 1; }
+      TRACE(1, j, 0);
+      if (j + 1 < n_steps) {
+        mbar_wait(&sml_full[st1], ph1);
+        TRACE(1, j, 1);
         tc_fence_after();
-        const uint32_t sds = smem_u32(smem + S::OFF_T0 + (j & 1) * S::T_BYTES);
-        const uint32_t sk = smem_u32(smem + S::OFF_SML0 + st * S::SML_BYTES);
+        issue_s_dp((j + 1) & 1, st1);
+      }
+      TRACE(1, j, 2);
+      mbar_wait(&t_ready[j & 1], (j >> 1) & 1);
+      TRACE(1, j, 3);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = dsc_ds + uint64_t(j & 1) * (S::T_BYTES >> 4);
+        const uint64_t db = dsc_kmn + uint64_t(st) * (S::SML_BYTES >> 4);
 #pragma unroll
         for (int kk = 0; kk < AB_BN / 16; ++kk)
-          umma_bf16(tmem_base + TM_DQ, make_smem_desc_sw128(sds + kk * 32, 0, 1024),
-                    make_smem_desc_sw128(sk + kk * 2048, AB_BN * 128, 1024), IDESC_DQ, (j | kk) != 0);
+          umma_bf16(tmem_base + TM_DQ, da + ((kk * 32) >> 4), db + ((kk * 2048) >> 4), IDESC_DQ, (j | kk) != 0);
         umma_commit(&sml_empty[st]);
-        st = st1; ph = ph1;
       }
-      umma_commit(done);
+      __syncwarp();
+      TRACE(1, j, 4);
+      st = st1; ph = ph1;
     }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
   } else {
     // ---- math warps: two threads per query row (warp w and w+4 share a TMEM lane quadrant, 32 key columns each)
     const int quad = warp & 3, half = warp >> 2;
@@ -225,12 +248,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const int sw = r_in & 7;
     for (int j = 0; j < n_steps; ++j) {
       const int buf = j & 1;
+      TRACE(0, j, 0);
       mbar_wait(&s_full[buf], (j >> 1) & 1);
+      TRACE(0, j, 1);
       tc_fence_after();
       uint32_t s[32], d[32];
       tmem_ld32(t_lane + TM_S + buf * 128 + half * 32, s);
       tmem_ld32(t_lane + TM_S + buf * 128 + 64 + half * 32, d);
       tmem_ld_wait();
+      TRACE(0, j, 2);
       const int c0 = j * AB_BN + half * 32;
       const bool need_mask = (p.causal && j * AB_BN + AB_BN - 1 > q0) || (j * AB_BN + AB_BN > p.seq_kv) || mrow;
       uint32_t pk[16];
@@ -260,9 +286,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       for (int ch = 0; ch < 4; ++ch)
         *reinterpret_cast<uint4*>(sds + (((half * 4 + ch) ^ sw) << 4)) =
             make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+      TRACE(0, j, 3);
       fence_proxy_async();
+      TRACE(0, j, 4);
       tc_fence_before();
       mbar_arrive(&t_ready[buf]);
+      TRACE(0, j, 5);
     }
     // ---- epilogue: the two threads of a row take alternate 32-column chunks of dQ
     mbar_wait(done, 0);
@@ -369,60 +398,65 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       }
     }
   } else if (warp == AB_W_MMA) {
-    if (lane == 0) {
-      auto issue_st_dpt = [&](int buf, int st) {
-        const uint32_t sk = smem_u32(smem + S::OFF_BIG0), sv = smem_u32(smem + S::OFF_BIG1);
-        const uint32_t sq = smem_u32(smem + S::OFF_SML0 + st * S::SML_BYTES);
-        const uint32_t sdo = smem_u32(smem + S::OFF_SML1 + st * S::SML_BYTES);
+    const uint64_t dsc_k = make_smem_desc_sw128(smem_u32(smem + S::OFF_BIG0), 0, 1024);
+    const uint64_t dsc_v = make_smem_desc_sw128(smem_u32(smem + S::OFF_BIG1), 0, 1024);
+    const uint64_t dsc_q = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML0), 0, 1024);           // K-major view (S^T)
+    const uint64_t dsc_do = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML1), 0, 1024);
+    const uint64_t dsc_qmn = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML0), AB_BN * 128, 1024);  // MN-major view (dK)
+    const uint64_t dsc_domn = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML1), AB_BN * 128, 1024); // MN-major view (dV)
+    const uint64_t dsc_pt = make_smem_desc_sw128(smem_u32(smem + S::OFF_T0), 0, 1024);
+    const uint64_t dsc_dst = make_smem_desc_sw128(smem_u32(smem + S::OFF_T1), 0, 1024);
+    auto issue_st_dpt = [&](int buf, int st) {
+      if (elect_one()) {
+        const uint64_t sto = uint64_t(st) * (S::SML_BYTES >> 4);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t oa = (kk / 4) * (AB_BM * 128) + (kk % 4) * 32, ob = (kk / 4) * (AB_BN * 128) + (kk % 4) * 32;
-          umma_bf16(tmem_base + TM_S + buf * 128, make_smem_desc_sw128(sk + oa, 0, 1024),
-                    make_smem_desc_sw128(sq + ob, 0, 1024), IDESC_S, kk != 0);
+          const uint32_t oa = ((kk / 4) * (AB_BM * 128) + (kk % 4) * 32) >> 4, ob = ((kk / 4) * (AB_BN * 128) + (kk % 4) * 32) >> 4;
+          umma_bf16(tmem_base + TM_S + buf * 128, dsc_k + oa, dsc_q + sto + ob, IDESC_S, kk != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t oa = (kk / 4) * (AB_BM * 128) + (kk % 4) * 32, ob = (kk / 4) * (AB_BN * 128) + (kk % 4) * 32;
-          umma_bf16(tmem_base + TM_S + buf * 128 + 64, make_smem_desc_sw128(sv + oa, 0, 1024),
-                    make_smem_desc_sw128(sdo + ob, 0, 1024), IDESC_S, kk != 0);
+          const uint32_t oa = ((kk / 4) * (AB_BM * 128) + (kk % 4) * 32) >> 4, ob = ((kk / 4) * (AB_BN * 128) + (kk % 4) * 32) >> 4;
+          umma_bf16(tmem_base + TM_S + buf * 128 + 64, dsc_v + oa, dsc_do + sto + ob, IDESC_S, kk != 0);
         }
-      };
-      mbar_wait(big_full, 0);
-      if (n_steps > 0) {
-        mbar_wait(&sml_full[0], 0);
-        tc_fence_after();
-        issue_st_dpt(0, 0);
-        umma_commit(&s_full[0]);
+        umma_commit(&s_full[buf]);
       }
-      int st = 0; uint32_t ph = 0;
-      for (int i = 0; i < n_steps; ++i) {
-        int st1 = st + 1; uint32_t ph1 = ph;
-        if (st1 == STAGES) { st1 = 0; ph1 ^= 1; }
-        if (i + 1 < n_steps) {
-          mbar_wait(&sml_full[st1], ph1);
-          tc_fence_after();
-          issue_st_dpt((i + 1) & 1, st1);
-          umma_commit(&s_full[(i + 1) & 1]);
-        }
-        mbar_wait(&t_ready[i & 1], (i >> 1) & 1);
-        tc_fence_after();
-        const uint32_t spt = smem_u32(smem + S::OFF_T0 + (i & 1) * S::T_BYTES);
-        const uint32_t sdst = smem_u32(smem + S::OFF_T1 + (i & 1) * S::T_BYTES);
-        const uint32_t sq = smem_u32(smem + S::OFF_SML0 + st * S::SML_BYTES);
-        const uint32_t sdo = smem_u32(smem + S::OFF_SML1 + st * S::SML_BYTES);
-#pragma unroll
-        for (int kk = 0; kk < AB_BN / 16; ++kk)
-          umma_bf16(tmem_base + TM_DV, make_smem_desc_sw128(spt + kk * 32, 0, 1024),
-                    make_smem_desc_sw128(sdo + kk * 2048, AB_BN * 128, 1024), IDESC_DKV, (i | kk) != 0);
-#pragma unroll
-        for (int kk = 0; kk < AB_BN / 16; ++kk)
-          umma_bf16(tmem_base + TM_DK, make_smem_desc_sw128(sdst + kk * 32, 0, 1024),
-                    make_smem_desc_sw128(sq + kk * 2048, AB_BN * 128, 1024), IDESC_DKV, (i | kk) != 0);
-        umma_commit(&sml_empty[st]);
-        st = st1; ph = ph1;
-      }
-      umma_commit(done);
+      __syncwarp();
+    };
+    mbar_wait(big_full, 0);
+    if (n_steps > 0) {
+      mbar_wait(&sml_full[0], 0);
+      tc_fence_after();
+      issue_st_dpt(0, 0);
     }
+    int st = 0; uint32_t ph = 0;
+    for (int i = 0; i < n_steps; ++i) {
+      int st1 = st + 1; uint32_t ph1 = ph;
+      if (st1 == STAGES) { st1 = 0; ph1 ^= 1; }
+      if (i + 1 < n_steps) {
+        mbar_wait(&sml_full[st1], ph1);
+        tc_fence_after();
+        issue_st_dpt((i + 1) & 1, st1);
+      }
+      mbar_wait(&t_ready[i & 1], (i >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t tb = uint64_t(i & 1) * (S::T_BYTES >> 4), sto = uint64_t(st) * (S::SML_BYTES >> 4);
+#pragma unroll
+        for (int kk = 0; kk < AB_BN / 16; ++kk)
+          umma_bf16(tmem_base + TM_DV, dsc_pt + tb + ((kk * 32) >> 4), dsc_domn + sto + ((kk * 2048) >> 4), IDESC_DKV,
+                    (i | kk) != 0);
+#pragma unroll
+        for (int kk = 0; kk < AB_BN / 16; ++kk)
+          umma_bf16(tmem_base + TM_DK, dsc_dst + tb + ((kk * 32) >> 4), dsc_qmn + sto + ((kk * 2048) >> 4), IDESC_DKV,
+                    (i | kk) != 0);
+        umma_commit(&sml_empty[st]);
+      }
+      __syncwarp();
+      st = st1; ph = ph1;
+    }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
   } else {
     // ---- math warps: two threads per KEY row (32 query columns each)
     const int quad = warp & 3, half = warp >> 2;
@@ -579,6 +613,12 @@ static int launch_attn_bwd(const void* q, const void* k, const void* v, const vo
 }  // namespace fsb
 
 using namespace fsb;
+
+#ifdef FSB_ATTN_TRACE
+extern "C" int fsb_debug_attn_trace(long long* host_out /* [2][64][8] */) {
+  return cudaMemcpyFromSymbol(host_out, g_attn_trace, sizeof(long long) * 2 * 64 * 8) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int fsb_sdpa_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
                             const float* lse, float* delta, void* dq, void* dk, void* dv, int64_t batch, int64_t seq_q,

@@ -153,36 +153,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                       j * ATT_BKV, b);
         if (++st == STAGES) { st = 0; ph ^= 1; }
       }
-    } else if (warp == 9 && lane == 0) {
-      // ===================== MMA issuer =====================
-      auto issue_S = [&](int slot, int st) {
-        const uint32_t sq = smem_u32(smem + S::OFF_Q + slot * S::Q_BYTES);
-        const uint32_t sk = smem_u32(smem + S::OFF_K + st * S::KV_BYTES);
+    } else if (warp == 9) {
+      // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
+      const uint64_t dsc_q = make_smem_desc_sw128(smem_u32(smem + S::OFF_Q), 0, 1024);
+      const uint64_t dsc_k = make_smem_desc_sw128(smem_u32(smem + S::OFF_K), 0, 1024);
+      const uint64_t dsc_p = make_smem_desc_sw128(smem_u32(smem + S::OFF_P), 0, 1024);
+      const uint64_t dsc_v = make_smem_desc_sw128(smem_u32(smem + S::OFF_V), ATT_BKV * 128, 1024);  // MN-major
+      auto issue_S = [&](int slot, int st) {   // caller: inside elect_one()
+        const uint64_t da = dsc_q + uint64_t(slot) * (S::Q_BYTES >> 4), db = dsc_k + uint64_t(st) * (S::KV_BYTES >> 4);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint64_t da = make_smem_desc_sw128(sq + (kk / 4) * (ATT_BQ * 128) + (kk % 4) * 32, 0, 1024);
-          const uint64_t db = make_smem_desc_sw128(sk + (kk / 4) * (ATT_BKV * 128) + (kk % 4) * 32, 0, 1024);
-          umma_bf16(tmem_base + TM_S + slot * ATT_BKV, da, db, IDESC_S, kk != 0);
-        }
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_bf16(tmem_base + TM_S + slot * ATT_BKV, da + (((kk / 4) * (ATT_BQ * 128) + (kk % 4) * 32) >> 4),
+                    db + (((kk / 4) * (ATT_BKV * 128) + (kk % 4) * 32) >> 4), IDESC_S, kk != 0);
       };
       auto issue_PV = [&](int slot, int st) {
-        const uint32_t sp = smem_u32(smem + S::OFF_P + slot * S::P_BYTES);
-        const uint32_t sv = smem_u32(smem + S::OFF_V + st * S::KV_BYTES);
+        const uint64_t da = dsc_p + uint64_t(slot) * (S::P_BYTES >> 4), db = dsc_v + uint64_t(st) * (S::KV_BYTES >> 4);
 #pragma unroll
-        for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
-          const uint64_t da = make_smem_desc_sw128(sp + kk * 32, 0, 1024);
-          const uint64_t db = make_smem_desc_sw128(sv + kk * 2048, ATT_BKV * 128, 1024);
-          umma_bf16(tmem_base + TM_O + slot * D, da, db, IDESC_PV, kk != 0);
-        }
+        for (int kk = 0; kk < ATT_BKV / 16; ++kk)
+          umma_bf16(tmem_base + TM_O + slot * D, da + ((kk * 32) >> 4), db + ((kk * 2048) >> 4), IDESC_PV, kk != 0);
       };
       mbar_wait(q_full, 0);
       int st = 0; uint32_t ph = 0;
       if (n_total > 0) {
         mbar_wait(&k_full[0], 0);
         tc_fence_after();
-        for (int i = 0; i < ATT_NQ; ++i)
-          if (n_kv[i] > 0) { issue_S(i, 0); umma_commit(&s_full[i]); }
-        umma_commit(&k_empty[0]);
+        if (elect_one()) {
+          for (int i = 0; i < ATT_NQ; ++i)
+            if (n_kv[i] > 0) { issue_S(i, 0); umma_commit(&s_full[i]); }
+          umma_commit(&k_empty[0]);
+        }
+        __syncwarp();
       }
       for (int j = 0; j < n_total; ++j) {
         int st1 = st + 1; uint32_t ph1 = ph;
@@ -192,18 +192,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (j >= n_kv[i]) continue;
           mbar_wait(&p_ready[i], j & 1);
           if (!v_waited) { mbar_wait(&v_full[st], ph); v_waited = true; }
+          const bool more = j + 1 < n_kv[i];
+          if (more) mbar_wait(&k_full[st1], ph1);
           tc_fence_after();
-          issue_PV(i, st);
-          umma_commit(&o_full[i]);
-          if (j + 1 < n_kv[i]) {
-            mbar_wait(&k_full[st1], ph1);
-            tc_fence_after();
-            issue_S(i, st1);
-            umma_commit(&s_full[i]);
+          if (elect_one()) {
+            issue_PV(i, st);
+            umma_commit(&o_full[i]);
+            if (more) { issue_S(i, st1); umma_commit(&s_full[i]); }
           }
+          __syncwarp();
         }
-        umma_commit(&v_empty[st]);
-        if (j + 1 < n_total) umma_commit(&k_empty[st1]);
+        if (elect_one()) {
+          umma_commit(&v_empty[st]);
+          if (j + 1 < n_total) umma_commit(&k_empty[st1]);
+        }
+        __syncwarp();
         st = st1; ph = ph1;
       }
     }

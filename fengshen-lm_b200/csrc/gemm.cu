@@ -141,35 +141,36 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
+    const uint64_t dsc_a = A_MN ? make_smem_desc_sw128(smem_u32(smem), GEMM_BK * 128, 1024)
+                                : make_smem_desc_sw128(smem_u32(smem), 0, 1024);
+    const uint64_t dsc_b = B_MN ? make_smem_desc_sw128(smem_u32(smem) + S::A_BYTES, GEMM_BK * 128, 1024)
+                                : make_smem_desc_sw128(smem_u32(smem) + S::A_BYTES, 0, 1024);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint32_t sb = sa + S::A_BYTES;
+        if (elect_one()) {
+          const uint64_t so = uint64_t(stage) * (S::STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, GEMM_BK * 128, 1024)
-                                     : make_smem_desc_sw128(sa + k * 32, 0, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, GEMM_BK * 128, 1024)
-                                     : make_smem_desc_sw128(sb + k * 32, 0, 1024);
-            umma_bf16(d_tmem, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < GEMM_BK / 16; ++k)
+            umma_bf16(d_tmem, dsc_a + so + ((A_MN ? k * 2048 : k * 32) >> 4), dsc_b + so + ((B_MN ? k * 2048 : k * 32) >> 4),
+                      IDESC, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================

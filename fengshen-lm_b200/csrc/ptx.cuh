@@ -12,6 +12,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+// One lane of a CONVERGED warp. Role loops are written warp-uniform with the single-thread instructions (TMA, tcgen05.mma,
+// commit) predicated on this: uniform control flow lets the compiler keep descriptors in uniform registers, which is what
+// UTCHMMA / UTMALDG take — a loop run under `if (lane == 0)` pays an R2UR chain per instruction instead (measured:
+// ~65-130 cycles per issued MMA in the attention kernels).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 // ----------------------------------------------------------------------------------------------
 // mbarrier
