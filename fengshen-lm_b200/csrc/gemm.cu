@@ -30,6 +30,7 @@ struct GemmParams {
   int bias_f32;    // bias dtype
   int epilogue;    // fsb_gemm_epilogue
   int accumulate;  // D += result
+  int tma_store;   // bf16 D without accumulate: stage through smem and write with cp.async.bulk.tensor (full lines)
   int tiles_m, tiles_n;
 };
 
@@ -39,7 +40,9 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;       // 2 x [128 rows x 64 cols] bf16 staging tiles (TMA store)
+  static constexpr int STORE_BYTES = GEMM_BM * 64 * 2;
+  static constexpr int BAR_OFFSET = STORE_OFFSET + 2 * STORE_BYTES;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024 /*align slack*/;
 };
@@ -67,7 +70,7 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
 template <int kLayout, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
   constexpr bool A_MN = (kLayout == FSB_GEMM_TN);
   constexpr bool B_MN = (kLayout != FSB_GEMM_NT);
   using S = GemmSmem<BN>;
@@ -175,6 +178,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32)
+    const int r_in = quad * 32 + lane;
+    const bool store_leader = (warp == 2 && lane == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -228,7 +233,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
         }
-        if (row_ok) {
+        if (p.tma_store) {
+          // smem-staged, 128B-swizzled [128 x 64] tile per 64-column group, written back by one bulk tensor store
+          const int g = c >> 1, hb = c & 1;
+          uint8_t* stg = smem + S::STORE_OFFSET + (g & 1) * S::STORE_BYTES;
+          if (hb == 0) {  // buffer (g & 1) was last used two groups ago: its store must have finished READING smem
+            if (store_leader) tma_store_wait_read<1>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 w;
+            w.x = pack_bf16x2(v[q * 8], v[q * 8 + 1]); w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]); w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            *reinterpret_cast<uint4*>(stg + r_in * 128 + (((hb * 4 + q) ^ (r_in & 7)) << 4)) = w;
+          }
+          if (hb == 1 || col0 + 32 >= p.N) {  // group complete (CTA-uniform)
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (store_leader) {
+              tma_store_3d(&tmD, stg, n0 + g * 64, m_idx * GEMM_BM, b);
+              tma_store_commit();
+            }
+          }
+        } else if (row_ok) {
           if (p.d_f32) {
             float* dp = reinterpret_cast<float*>(p.D) + int64_t(b) * p.stride_d + int64_t(row) * p.ldd + col0;
             if (full_cols) {
@@ -274,6 +302,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && store_leader) tma_store_wait_read<0>();  // smem must outlive the last bulk store's reads
   }
 
   tc_fence_before();
@@ -285,7 +314,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int kLayout, int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const GemmParams& p,
+                       cudaStream_t stream) {
   using S = GemmSmem<BN>;
   static bool configured = false;
   auto kern = gemm_bf16_kernel<kLayout, BN>;
@@ -299,7 +329,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   }
   const int num_tiles = p.tiles_m * p.tiles_n * p.batch;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmD, p);
   FSB_CUDA_LAUNCH_CHECK();
   return FSB_OK;
 }
@@ -348,6 +378,15 @@ extern "C" int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K, const 
     if (rc) return rc;
   }
   GemmParams p;
+  p.tma_store = (d_dtype == FSB_BF16 && !accumulate) ? 1 : 0;
+  CUtensorMap tmD = tmA;  // placeholder when the bulk-store path is off
+  if (p.tma_store) {
+    uint64_t dims[3] = {uint64_t(N), uint64_t(M), uint64_t(batch)};
+    uint64_t strides[2] = {uint64_t(ldd) * 2, uint64_t(batch > 1 ? stride_d : M * ldd) * 2};
+    uint32_t box[3] = {64, uint32_t(GEMM_BM), 1};
+    int rc = make_tmap_bf16(&tmD, D, 3, dims, strides, box);
+    if (rc) return rc;
+  }
   p.D = D; p.aux = aux; p.bias = bias;
   p.ldd = ldd; p.ldaux = ldaux; p.stride_d = stride_d; p.stride_aux = stride_aux;
   p.M = int(M); p.N = int(N); p.K = int(K); p.batch = int(batch);
@@ -358,7 +397,7 @@ extern "C" int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K, const 
 
 #define FSB_GEMM_DISPATCH(L)                                                    \
   case L:                                                                        \
-    return BN == 256 ? launch_gemm<L, 256>(tmA, tmB, p, stream) : launch_gemm<L, 128>(tmA, tmB, p, stream);
+    return BN == 256 ? launch_gemm<L, 256>(tmA, tmB, tmD, p, stream) : launch_gemm<L, 128>(tmA, tmB, tmD, p, stream);
   switch (layout) {
     FSB_GEMM_DISPATCH(FSB_GEMM_NT)
     FSB_GEMM_DISPATCH(FSB_GEMM_NN)

@@ -38,10 +38,14 @@ def _init_normal_(t, std, gen):
 
 
 class LlamaForCausalLM(nn.Module):
-    def __init__(self, config, device=None, world_size=1, seed=0):
+    def __init__(self, config, device=None, world_size=None, seed=0):
         super().__init__()
         self.config = config
-        dev = torch.device(device if device is not None else "cuda")
+        if world_size is None:  # laid out for the job's data-parallel world (the scripts build the model in setup())
+            import torch.distributed as dist
+            world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}"
+                           if torch.cuda.is_available() else "cuda")
         if dev.type != "cuda":
             raise RuntimeError("fsb200 LlamaForCausalLM runs on CUDA only (no CPU fallback on the product path)")
         h, V, nl, nh = config.hidden_size, config.vocab_size, config.num_hidden_layers, config.num_attention_heads
@@ -136,6 +140,23 @@ class LlamaForCausalLM(nn.Module):
                 _init_normal_(prm.data, wang, gen)
             else:
                 _init_normal_(prm.data, small, gen)
+
+    # The reference scripts call `.from_pretrained(..., torch_dtype=torch.half).cuda()`; parameters here are views into the
+    # flat bf16 CUDA buffer and must never be re-allocated by nn.Module._apply.
+    def cuda(self, device=None):
+        return self
+
+    def half(self):
+        return self
+
+    def bfloat16(self):
+        return self
+
+    def to(self, *args, **kwargs):
+        return self
+
+    def train(self, mode=True):   # reference defect (modeling_llama.py:257-260: `mode` is required there); accept both
+        return super().train(mode)
 
     # HF-style loading of a reference state dict (fp32/fp16/bf16 tensors on any device)
     @torch.no_grad()
