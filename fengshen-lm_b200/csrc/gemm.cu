@@ -361,7 +361,10 @@ extern "C" int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K, const 
   // Tensor maps: always rank 3 (inner, outer, batch).
   CUtensorMap tmA, tmB;
   const bool a_mn = (layout == FSB_GEMM_TN), b_mn = (layout != FSB_GEMM_NT);
-  const int BN = (N > 128) ? 256 : 128;
+  // 128 x 256 tiles unless they would leave a large part of the 148 SMs idle (weight-gradient GEMMs of small models:
+  // e.g. 768 x 2304 x 32768 is only 54 such tiles) — then 128 x 128 tiles double the parallelism.
+  const int64_t tiles256 = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + 255) / 256) * batch;
+  const int BN = (N > 128 && tiles256 * 10 >= int64_t(num_sms()) * 7) ? 256 : 128;
   {
     // A: K-major -> memory [M rows, K inner]; MN-major -> memory [K rows, M inner]
     uint64_t dims[3] = {uint64_t(a_mn ? M : K), uint64_t(a_mn ? K : M), uint64_t(batch)};

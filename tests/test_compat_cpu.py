@@ -1,0 +1,150 @@
+"""CPU: the drop-in surface (fengshen-lm_b200/compat) — import paths, argparse flags, sampler index arithmetic,
+optimizer/scheduler construction and strategy config discovery behave like the reference (cited per test).
+No CUDA is touched: the model itself is exercised by the -m gpu tests."""
+import argparse
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COMPAT = os.path.join(ROOT, "fengshen-lm_b200", "compat")
+if COMPAT not in sys.path:
+    sys.path.insert(0, COMPAT)
+
+import pytorch_lightning as pl  # noqa: E402
+from fengshen.data.universal_datamodule import PretrainingRandomSampler, PretrainingSampler, UniversalDataModule  # noqa: E402
+from fengshen.models import model_utils  # noqa: E402
+from fengshen.strategies.megatron_deepspeed import DeepSpeedStrategy  # noqa: E402
+from fengshen.utils.universal_checkpoint import UniversalCheckpoint  # noqa: E402
+
+
+def _parser():
+    p = argparse.ArgumentParser()
+    p = model_utils.add_module_args(p)
+    p = pl.Trainer.add_argparse_args(p)
+    p = UniversalDataModule.add_data_specific_args(p)
+    p = UniversalCheckpoint.add_argparse_args(p)
+    return p
+
+
+def test_argparse_surface_matches_reference_flags_and_defaults():
+    a = _parser().parse_args([])
+    # fengshen/models/model_utils.py:13-28
+    assert (a.learning_rate, a.min_learning_rate, a.warmup_ratio, a.weight_decay) == (5e-5, 1e-7, 0.1, 0.1)
+    assert (a.adam_beta1, a.adam_beta2, a.adam_epsilon, a.scheduler_type) == (0.9, 0.999, 1e-8, "polynomial")
+    # universal_datamodule.py:22-45, universal_checkpoint.py:7-21
+    assert (a.train_batchsize, a.sampler_type, a.use_mpu) == (16, "random", False)
+    assert (a.monitor, a.save_ckpt_path, a.save_top_k) == ("step", "./ckpt/", 10)
+    assert a.max_steps == -1 and a.accumulate_grad_batches == 1
+
+
+def test_pretraining_sampler_partitions_global_batches_by_rank():
+    # universal_sampler.py:22-68
+    got = [list(PretrainingSampler(20, 4, 2, r, 2)) for r in (0, 1)]
+    assert got[0] == [[4, 5], [8, 9], [12, 13], [16, 17]]
+    assert got[1] == [[6, 7], [10, 11], [14, 15], [18, 19]]
+    assert len(PretrainingSampler(20, 0, 2, 0, 2)) == 5
+
+
+def test_pretraining_random_sampler_buckets_and_resume():
+    # universal_sampler.py:71-125: rank r owns bucket r; a resumed sampler continues inside the same permutation
+    full = [list(PretrainingRandomSampler(40, 0, 2, r, 2, epoch=3)) for r in (0, 1)]
+    flat0 = [i for b in full[0] for i in b]
+    flat1 = [i for b in full[1] for i in b]
+    assert sorted(flat0) == list(range(0, 20)) and sorted(flat1) == list(range(20, 40))
+    resumed = list(PretrainingRandomSampler(40, 8, 2, 0, 2, epoch=3))   # 8 consumed samples = 2 global batches
+    assert resumed == full[0][2:]
+    other_epoch = [i for b in PretrainingRandomSampler(40, 0, 2, 0, 2, epoch=4) for i in b]
+    assert other_epoch != flat0 and sorted(other_epoch) == sorted(flat0)
+
+
+class _Lit(pl.LightningModule):
+    def __init__(self, args):
+        super().__init__()
+        self.save_hyperparameters(args)
+        self.layer = torch.nn.Linear(4, 4)
+        self.input_layernorm = torch.nn.Module()
+        self.input_layernorm.scale = torch.nn.Parameter(torch.ones(4))
+        self.total_steps = 100
+
+
+def test_configure_optimizers_groups_by_name_and_builds_polynomial_schedule():
+    a = _parser().parse_args(["--learning_rate", "1e-3", "--warmup_steps", "10", "--adam_beta2", "0.95"])
+    m = _Lit(a)
+    m.trainer = pl.Trainer(strategy=DeepSpeedStrategy(pipe_model_parallel_size=1, tensor_model_parallel_size=1, mpu_seed=42))
+    (opt,), (sch,) = model_utils.configure_optimizers(m)
+    assert type(opt).__name__ == "FusedAdam"                       # model_utils.py:69-72
+    assert sch["interval"] == "step" and sch["frequency"] == 1     # :97
+    decay, no_decay = opt.param_groups
+    assert decay["weight_decay"] == 0.1 and no_decay["weight_decay"] == 0.0
+    assert len(decay["params"]) == 1 and len(no_decay["params"]) == 2   # weight | bias + layernorm.scale (:39-47)
+    assert opt.param_groups[0]["betas"] == (0.9, 0.95)
+    from fsb200.schedules import polynomial_lr
+    for step in range(0, 120, 7):
+        assert abs(opt.param_groups[0]["lr"] - polynomial_lr(step, 1e-3, 10, 100, 1e-7)) < 1e-12
+        for _ in range(7):
+            opt.step(); sch["scheduler"].step()
+
+
+def test_ddp_strategy_selects_adamw():
+    a = _parser().parse_args([])
+    m = _Lit(a)
+    m.trainer = pl.Trainer(strategy="ddp")
+    (opt,), _ = model_utils.configure_optimizers(m)
+    assert isinstance(opt, torch.optim.AdamW)                      # model_utils.py:80-83
+
+
+def test_get_total_steps_integer_arithmetic():
+    # model_utils.py:194-209
+    a = _parser().parse_args(["--max_epochs", "3", "--train_batchsize", "4", "--accumulate_grad_batches", "2"])
+    tr = pl.Trainer.from_argparse_args(a)
+    tr.world_size = 2
+    tr._train_loader = torch.utils.data.DataLoader(list(range(101)), batch_size=4)
+    assert model_utils.get_total_steps(tr, a) == (101 * 3 // 8) // 2
+    a2 = _parser().parse_args(["--max_epochs", "-1", "--max_steps", "77"])
+    tr2 = pl.Trainer.from_argparse_args(a2)
+    tr2._train_loader = tr._train_loader
+    assert model_utils.get_total_steps(tr2, a2) == 77
+
+
+def test_strategy_reads_deepspeed_json_from_env(tmp_path, monkeypatch):
+    cfg = {"zero_optimization": {"stage": 2, "reduce_bucket_size": 2e8}, "gradient_clipping": 1,
+           "bf16": {"enabled": True}, "activation_checkpointing": {"partition_activations": False}}
+    path = tmp_path / "ds.json"
+    path.write_text(json.dumps(cfg))
+    monkeypatch.setenv("PL_DEEPSPEED_CONFIG_PATH", str(path))          # megatron_deepspeed.py:53
+    s = DeepSpeedStrategy(tensor_model_parallel_size=1, pipe_model_parallel_size=1, mpu_seed=42)
+    assert s.stage == 2 and s.gradient_clipping == 1.0 and s.precision == "bf16"
+    assert "offload_optimizer" not in s.config["zero_optimization"]
+    with pytest.raises(NotImplementedError):
+        DeepSpeedStrategy(tensor_model_parallel_size=8, pipe_model_parallel_size=1, mpu_seed=42)
+    monkeypatch.setenv("PL_DEEPSPEED_CONFIG_PATH", str(tmp_path / "missing.json"))
+    with pytest.raises(FileNotFoundError):
+        DeepSpeedStrategy(tensor_model_parallel_size=1, pipe_model_parallel_size=1, mpu_seed=42)
+
+
+def test_strategy_registry_strings():
+    from pytorch_lightning.strategies import strategy_from_string
+    assert strategy_from_string("deepspeed_stage_1").stage == 1
+    assert strategy_from_string("deepspeed_stage_2").stage == 2
+    assert strategy_from_string("ddp").stage == 1
+    with pytest.raises(NotImplementedError):
+        strategy_from_string("deepspeed_stage_3")
+    with pytest.raises(NotImplementedError):
+        strategy_from_string("deepspeed_stage_2_offload")
+
+
+def test_universal_checkpoint_drops_missing_resume_path(tmp_path):
+    a = _parser().parse_args(["--load_ckpt_path", str(tmp_path / "nope"), "--save_ckpt_path", str(tmp_path)])
+    cb = UniversalCheckpoint(a)
+    assert a.load_ckpt_path is None and cb.dirpath == str(tmp_path)   # universal_checkpoint.py:37-41
+
+
+def test_example_script_parses_on_the_reference_surface():
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import importlib
+    mod = importlib.import_module("pretrain_ziya_llama")
+    assert hasattr(mod, "Llama") and hasattr(mod.Llama, "training_step")
