@@ -179,7 +179,7 @@ class Trainer:
                 self.just_stepped = False
                 if micro % self.accumulate_grad_batches == 0:
                     self.engine.step(lr=opt.param_groups[0]["lr"])
-                    opt._step_count = getattr(opt, "_step_count", 0) + 1  # keeps torch's LR-scheduler order check quiet
+                    opt.step()  # hyper-parameter carrier: a no-op (FusedAdam shim) or grad-less torch optimizer
                     for sc in self.lr_scheduler_configs:
                         if sc.get("interval", "epoch") == "step":
                             sc["scheduler"].step()

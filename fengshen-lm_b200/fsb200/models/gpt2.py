@@ -24,10 +24,14 @@ class _Holder(nn.Module):
 
 
 class GPT2LMHeadModel(nn.Module):
-    def __init__(self, config, device=None, world_size=1, seed=0):
+    def __init__(self, config, device=None, world_size=None, seed=0):
         super().__init__()
         self.config = config
-        dev = torch.device(device if device is not None else "cuda")
+        if world_size is None:
+            import torch.distributed as dist
+            world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}"
+                           if torch.cuda.is_available() else "cuda")
         if dev.type != "cuda":
             raise RuntimeError("fsb200 GPT2LMHeadModel runs on CUDA only (no CPU fallback on the product path)")
         g = lambda k, d=None: getattr(config, k, d)

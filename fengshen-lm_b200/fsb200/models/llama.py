@@ -129,17 +129,20 @@ class LlamaForCausalLM(nn.Module):
     # ---- init (layers/init_functions.py:121-142: small_init std sqrt(2/(5h)); wang_init std 2/(L*sqrt(h))) -------------
     @torch.no_grad()
     def reset_parameters(self, seed=0):
-        gen = torch.Generator().manual_seed(seed)
         h, nl = self.h, self.nl
         small = math.sqrt(2.0 / (5.0 * h))
         wang = 2.0 / (nl * math.sqrt(h))
+        big = self.flat.total > 300_000_000  # billions of CPU randn take minutes: draw on the device instead
+        gen = torch.Generator(device=self.flat.params.device if big else "cpu").manual_seed(seed)
         for name, prm in self.named_parameters():
             if name.endswith(".scale"):
                 prm.fill_(1.0)
-            elif name.endswith("dense.weight") or name.endswith("w2.weight"):
-                _init_normal_(prm.data, wang, gen)
+                continue
+            std = wang if (name.endswith("dense.weight") or name.endswith("w2.weight")) else small
+            if big:
+                prm.normal_(0.0, std, generator=gen)
             else:
-                _init_normal_(prm.data, small, gen)
+                _init_normal_(prm.data, std, gen)
 
     # The reference scripts call `.from_pretrained(..., torch_dtype=torch.half).cuda()`; parameters here are views into the
     # flat bf16 CUDA buffer and must never be re-allocated by nn.Module._apply.

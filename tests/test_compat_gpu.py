@@ -28,8 +28,8 @@ def test_example_script_trains_checkpoints_and_resumes(tmp_path):
     import pretrain_ziya_llama as ex
     trainer, module = ex.main(_args(tmp_path))
     assert trainer.global_step == 12
-    losses = [float(l.split('"train/loss": ')[1].split(",")[0].rstrip("}")) for l in
-              open(os.path.join(trainer.logger.save_dir, "metrics.jsonl"))]
+    import json
+    losses = [json.loads(l)["train/loss"] for l in open(os.path.join(trainer.logger.save_dir, "metrics.jsonl"))]
     assert losses[-1] < losses[0] - 0.2, losses
     ck = tmp_path / "ckpt" / "last.ckpt" / "checkpoint"
     assert (ck / "mp_rank_00_model_states.pt").exists() and (ck / "zero_pp_rank_0_mp_rank_00_optim_states.pt").exists()
