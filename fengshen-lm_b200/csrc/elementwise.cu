@@ -71,18 +71,21 @@ __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + 
 __device__ __forceinline__ float dgelu_erf_f(float x) {
   return 0.5f * (1.f + erff(x * 0.7071067811865476f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
-// act: 0 silu, 1 gelu_tanh, 2 gelu_erf
+// act: 0 silu, 1 gelu_tanh, 2 gelu_erf, 3 tanh (BERT pooler, transformers bert/modeling_bert.py BertPooler)
 template <int ACT>
 __device__ __forceinline__ float act_f(float x) {
   if (ACT == 0) return x * sigmoid_f(x);
   if (ACT == 1) return gelu_tanh_f(x);
-  return gelu_erf_f(x);
+  if (ACT == 2) return gelu_erf_f(x);
+  return tanhf(x);
 }
 template <int ACT>
 __device__ __forceinline__ float dact_f(float x) {
   if (ACT == 0) { float s = sigmoid_f(x); return s * (1.f + x * (1.f - s)); }
   if (ACT == 1) return dgelu_tanh_f(x);
-  return dgelu_erf_f(x);
+  if (ACT == 2) return dgelu_erf_f(x);
+  const float t = tanhf(x);
+  return 1.f - t * t;
 }
 
 // out[t, c] = act(gate[t, c]) * up[t, c]; gate/up/out have independent row strides (elements).
@@ -351,20 +354,20 @@ extern "C" int fsb_glu_bwd(int act, const void* dout, const void* gate, const vo
   return FSB_OK;
 }
 extern "C" int fsb_act_fwd(int act, const void* x, void* y, int64_t n, fsb_stream_t st) {
-  FSB_REQUIRE(act >= 0 && act <= 2 && x && y && n > 0 && n % 8 == 0 && aligned16(x) && aligned16(y), "act_fwd: bad args");
+  FSB_REQUIRE(act >= 0 && act <= 3 && x && y && n > 0 && n % 8 == 0 && aligned16(x) && aligned16(y), "act_fwd: bad args");
   const int g = ew_grid(n / 8, 256);
 #define L(A) act_fwd_kernel<A><<<g, 256, 0, (cudaStream_t)st>>>((const uint4*)x, (uint4*)y, n / 8)
-  if (act == 0) L(0); else if (act == 1) L(1); else L(2);
+  if (act == 0) L(0); else if (act == 1) L(1); else if (act == 2) L(2); else L(3);
 #undef L
   FSB_CUDA_LAUNCH_CHECK();
   return FSB_OK;
 }
 extern "C" int fsb_act_bwd(int act, const void* dy, const void* x, void* dx, int64_t n, fsb_stream_t st) {
-  FSB_REQUIRE(act >= 0 && act <= 2 && dy && x && dx && n > 0 && n % 8 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx),
+  FSB_REQUIRE(act >= 0 && act <= 3 && dy && x && dx && n > 0 && n % 8 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx),
               "act_bwd: bad args");
   const int g = ew_grid(n / 8, 256);
 #define L(A) act_bwd_kernel<A><<<g, 256, 0, (cudaStream_t)st>>>((const uint4*)dy, (const uint4*)x, (uint4*)dx, n / 8)
-  if (act == 0) L(0); else if (act == 1) L(1); else L(2);
+  if (act == 0) L(0); else if (act == 1) L(1); else if (act == 2) L(2); else L(3);
 #undef L
   FSB_CUDA_LAUNCH_CHECK();
   return FSB_OK;

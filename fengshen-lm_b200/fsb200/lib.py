@@ -19,7 +19,7 @@ c_size = ctypes.c_size_t
 BF16, F32 = 0, 1
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
 EPI_NONE, EPI_GELU_TANH, EPI_GELU_ERF = 0, 1, 2
-ACT_SILU, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2
+ACT_SILU, ACT_GELU_TANH, ACT_GELU_ERF, ACT_TANH = 0, 1, 2, 3
 
 # name -> (restype, [argtypes])  — must mirror include/fsb200.h exactly (tests/test_abi.py checks the symbol list)
 SIGNATURES = {

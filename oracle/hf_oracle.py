@@ -32,6 +32,51 @@ def build_gpt2(cfg, seed=0, bf16_exact=True):
     return _bf16_exact_(model) if bf16_exact else model
 
 
+BERT_SMALL = dict(vocab_size=512, hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                  max_position_embeddings=128, type_vocab_size=2)
+
+
+def build_bert(cfg, seed=0, bf16_exact=True):
+    """BertForMaskedLM as examples/pretrain_bert/pretrain_bert.py:135-137 builds it (config -> random init)."""
+    from transformers import BertConfig, BertForMaskedLM
+    torch.manual_seed(seed)
+    config = BertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, hidden_act="gelu",
+                        attn_implementation="eager", **cfg)
+    model = BertForMaskedLM(config)
+    model.train()
+    return _bf16_exact_(model) if bf16_exact else model
+
+
+def build_megatron_bert(cfg, seed=0, bf16_exact=True, hidden_act="gelu"):
+    """MegatronBertForPreTraining as examples/pretrain_erlangshen_bert/pretrain_erlangshen.py:138-141 builds it."""
+    from transformers import MegatronBertConfig, MegatronBertForPreTraining
+    torch.manual_seed(seed)
+    config = MegatronBertConfig(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, hidden_act=hidden_act,
+                                attn_implementation="eager", **cfg)
+    model = MegatronBertForPreTraining(config)
+    model.train()
+    return _bf16_exact_(model) if bf16_exact else model
+
+
+def make_mlm_batch(V, B, S, seed=1234, nsp=False, pad_tail=0):
+    """Synthetic MLM batch: ids uniform in [1, V), labels = -100 except a Bernoulli(0.15) subset where
+    labels = ids; token types 0/1 split at the middle; optional NSP labels and a padded tail on the last sample."""
+    rs = np.random.RandomState(seed)
+    ids = torch.from_numpy(rs.randint(1, V, size=(B, S)).astype(np.int64))
+    sel = torch.from_numpy(rs.rand(B, S) < 0.15)
+    labels = torch.where(sel, ids, torch.full_like(ids, -100))
+    tt = torch.zeros_like(ids)
+    tt[:, S // 2:] = 1
+    am = torch.ones_like(ids)
+    if pad_tail:
+        am[-1, S - pad_tail:] = 0
+        labels[-1, S - pad_tail:] = -100
+    b = {"input_ids": ids, "attention_mask": am, "token_type_ids": tt, "labels": labels}
+    if nsp:
+        b["next_sentence_label"] = torch.from_numpy(rs.randint(0, 2, size=(B,)).astype(np.int64))
+    return b
+
+
 def make_lm_batch(V, B, S, seed=1234):
     """Synthetic causal-LM batch: labels = input_ids, attention_mask = 1."""
     rs = np.random.RandomState(seed)

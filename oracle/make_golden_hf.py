@@ -33,6 +33,13 @@ def main():
     rec["train_hparams"] = np.array([LR, 0.9, 0.999, 1e-8, WD])
     np.savez_compressed(os.path.join(OUT, "gpt2_small.npz"), **rec)
     print("gpt2_small: loss", out.loss.item(), "curve", rec["loss_curve"][0], "->", rec["loss_curve"][-1])
+    # BERT-family golden losses (same seeds as tests/test_bert_gpu.py)
+    Vb = H.BERT_SMALL["vocab_size"]
+    lb = H.build_bert(H.BERT_SMALL)(**H.make_mlm_batch(Vb, 3, 96, seed=5, pad_tail=20)).loss.item()
+    lm = H.build_megatron_bert(H.BERT_SMALL)(**H.make_mlm_batch(Vb, 3, 96, seed=6, nsp=True, pad_tail=11)).loss.item()
+    np.savez_compressed(os.path.join(OUT, "bert_small.npz"), bert_loss=np.array(lb), megatron_loss=np.array(lm),
+                        transformers_version=np.array(transformers.__version__))
+    print("bert_small: bert", lb, "megatron", lm)
 
 
 if __name__ == "__main__":
