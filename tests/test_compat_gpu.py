@@ -17,7 +17,7 @@ for p in (os.path.join(ROOT, "fengshen-lm_b200", "compat"), os.path.join(ROOT, "
 
 def _args(tmp, extra=()):
     return ["--hidden_size", "256", "--num_layers", "2", "--num_heads", "4", "--vocab_size", "512",
-            "--max_seq_length", "64", "--num_samples", "64", "--train_batchsize", "4", "--max_steps", "12",
+            "--max_seq_length", "64", "--num_samples", "8", "--train_batchsize", "4", "--max_steps", "12",
             "--max_epochs", "-1", "--learning_rate", "1e-3", "--adam_beta2", "0.95", "--warmup_steps", "2",
             "--strategy", "deepspeed_stage_2", "--default_root_dir", str(tmp), "--save_ckpt_path", str(tmp / "ckpt"),
             "--load_ckpt_path", str(tmp / "ckpt" / "last.ckpt"), "--every_n_train_steps", "6", "--save_last",
@@ -35,7 +35,7 @@ def test_example_script_trains_checkpoints_and_resumes(tmp_path):
     assert (ck / "mp_rank_00_model_states.pt").exists() and (ck / "zero_pp_rank_0_mp_rank_00_optim_states.pt").exists()
     state = torch.load(ck / "mp_rank_00_model_states.pt", map_location="cpu", weights_only=False)
     assert "module" in state and any(k.endswith("attention.query_key_value.weight") for k in state["module"])
-    assert state["global_samples"] == 12 * 4
+    assert state["global_samples"] == 12 * 4  # steps x micro-batch x world x GA
     w_before = module.model.flat.params.clone()
     # resume: continues at step 12 and trains 4 more steps from the saved weights / optimizer shard / LR schedule
     trainer2, module2 = ex.main(_args(tmp_path, ("--max_steps", "16")))

@@ -56,7 +56,9 @@ def _run(rank, world, port, q, ga):
             dist.all_reduce(t)
             t /= world
         losses.append(t.item())
-    q.put((world, rank, losses, model.flat.params.float().cpu()))
+    import hashlib
+    digest = hashlib.sha1(model.flat.params.view(torch.int16).cpu().numpy().tobytes()).hexdigest()
+    q.put((world, rank, losses, digest))   # plain Python objects only: the child may exit before the parent reads
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -79,8 +81,7 @@ def test_two_rank_zero_matches_single_gpu():
     p1.join(timeout=60)
     r0 = next(r for r in res if r[1] == 0)
     r1 = next(r for r in res if r[1] == 1)
-    # parameters are padded per world size: compare the named views through a fresh layout-independent checksum
-    assert torch.equal(r0[3], r1[3]), "ranks hold different parameters after the all-gather"
+    assert r0[3] == r1[3], "ranks hold different parameters after the all-gather"
     for a, b in zip(r0[2], single[2]):
         assert abs(a - b) < 5e-3, (r0[2], single[2])
     assert r0[2][-1] < r0[2][0]
