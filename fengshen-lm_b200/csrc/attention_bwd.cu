@@ -23,11 +23,6 @@ constexpr int AB_THREADS = 320;  // warps 0-7: math (2 threads per row, 32 colum
 constexpr int AB_MATH = 256;
 constexpr int AB_W_TMA = 8, AB_W_MMA = 9;
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 constexpr int AB_BM = 128;       // rows owned by the CTA (queries for dQ, keys for dKV) == TMEM lanes
 constexpr int AB_BN = 64;        // streamed tile (keys for dQ, queries for dKV)
 

@@ -5,13 +5,17 @@
 // without the three repacking copies of q/k/v (transformer.py:419-429): Q, K, V are read straight out of the packed
 // QKV projection output through TMA tensor maps (any row/head stride), O is written in [token, head*dim] layout.
 //
-// CTA = one (batch, head, pair of 128-row Q tiles). 12 warps:
-//   warps 0-3 / 4-7 : softmax warpgroup for Q tile 0 / 1 — ONE THREAD PER ROW (TMEM lane == row): no shuffles
-//   warp 8          : TMA producer (Q once, K/V tiles through a multi-stage ring)
-//   warp 9          : tcgen05.mma issuer  S_i = Q_i K_j^T  (128 x 64 x D)  and  O_i(j) = P_i V_j  (128 x D x 64)
-// The two Q tiles ping-pong: while warpgroup 0 does exp2 on S_0 the tensor core computes S_1 / PV_1 and vice versa.
-// P is written as bf16 into shared memory in the canonical K-major SWIZZLE_128B layout and fed back as the A operand;
-// V is consumed as an MN-major B operand straight from its row-major tile. O accumulates in registers (fp32).
+// CTA = one (batch, head, pair of 128-row Q tiles), 18 warps:
+//   warps 0-7 / 8-15 : softmax group of Q tile 0 / 1. TMEM lane == query row; the two threads of a row (warps w, w+4 of
+//                      the group share a lane quadrant) take 32 of the 64 key columns of a step each.
+//   warp 16          : TMA producer (Q once; K and V tiles through multi-stage rings)
+//   warp 17          : tcgen05.mma issuer: S_i(j) = Q_i K_j^T (128 x 64 x D), O_i += P_i(j) V_j (128 x D x 64)
+// S is double-buffered in TMEM and P in shared memory, so the tensor core runs S(j+1)/S(j+2) while the softmax group
+// works on step j; the two Q tiles interleave on top of that.
+// O ACCUMULATES IN TMEM across the whole key loop. The running max used as exponent reference (m_ref) is only raised
+// when the true row max exceeds it by more than 2^8 (lazy rescaling): then — rarely — the group multiplies its O rows
+// in TMEM by 2^(m_ref_old - m_new) (tcgen05.ld / tcgen05.st). Probabilities are therefore <= 256 instead of <= 1, well
+// inside bf16/fp32 range; the final O / l is exact in the same way as with the eager rescale.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -20,21 +24,25 @@ namespace fsb {
 constexpr int ATT_BQ = 128;   // rows per Q tile (= TMEM lanes)
 constexpr int ATT_NQ = 2;     // Q tiles per CTA
 constexpr int ATT_BKV = 64;   // keys per inner step
-constexpr int ATT_THREADS = 384;
+constexpr int ATT_GROUP = 256;                       // softmax threads per Q tile
+constexpr int ATT_THREADS = ATT_NQ * ATT_GROUP + 64; // + TMA warp + MMA warp
+constexpr int ATT_W_TMA = 16, ATT_W_MMA = 17;
+constexpr float ATT_RESCALE_TAU = 8.0f;              // log2 units
 
 template <int D>
 struct AttFwdSmem {
-  static constexpr int STAGES = (D == 128) ? 4 : 8;  // K/V ring depth: must cover the TMA round trip
-  static constexpr int Q_BYTES = ATT_BQ * D * 2;       // per slot
-  static constexpr int KV_BYTES = ATT_BKV * D * 2;     // per tensor per stage
-  static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2; // per slot
+  static constexpr int STAGES = (D == 128) ? 3 : 6;        // K/V ring depth (must cover the TMA round trip)
+  static constexpr int Q_BYTES = ATT_BQ * D * 2;           // per slot
+  static constexpr int KV_BYTES = ATT_BKV * D * 2;         // per tensor per stage
+  static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2;     // per slot per buffer
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + ATT_NQ * Q_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * KV_BYTES;
-  static constexpr int OFF_P = OFF_V + STAGES * KV_BYTES;
-  static constexpr int OFF_BAR = OFF_P + ATT_NQ * P_BYTES;
-  // q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2], p_ready[2], o_full[2]
-  static constexpr int NBAR = 1 + 4 * STAGES + 6;
+  static constexpr int OFF_P = OFF_V + STAGES * KV_BYTES;  // [slot][buf]
+  static constexpr int OFF_RED = OFF_P + ATT_NQ * 2 * P_BYTES;  // float [slot][half][128]: row max / row sum exchange
+  static constexpr int OFF_BAR = OFF_RED + ATT_NQ * 2 * ATT_BQ * 4;
+  // q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2][2], p_ready[2], o_done[2]
+  static constexpr int NBAR = 1 + 4 * STAGES + 8;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
 };
 
@@ -43,22 +51,11 @@ struct AttFwdParams {
   float* lse;               // [batch, nheads, seq_q], log2 domain
   const uint8_t* kv_mask;   // [batch, seq_kv] (1 = attend) or nullptr
   int64_t o_row_stride, o_head_stride;
-  int q_col0, k_col0, v_col0;           // column (element) offset of head 0 inside each tensor map
   int q_head_stride, k_head_stride, v_head_stride;
   int seq_q, seq_kv, nheads, batch;
   int causal;
   float scale_log2;  // softmax scale * log2(e)
 };
-
-__device__ __forceinline__ float ex2_approx_f(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-template <int kRegs>
-__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs)); }
-template <int kRegs>
-__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs)); }
 
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -66,11 +63,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmV, const AttFwdParams p) {
   using S = AttFwdSmem<D>;
   constexpr int STAGES = S::STAGES;
-  constexpr int TMEM_COLS = (D == 128) ? 512 : 256;
-  constexpr int TM_S = 0;                 // S_i at TM_S + i*64
-  constexpr int TM_O = ATT_NQ * ATT_BKV;  // O_i at TM_O + i*D
+  constexpr int TMEM_COLS = 512;
+  constexpr int SLOT_COLS = 2 * ATT_BKV + D;  // S[2] | O   per Q tile
   constexpr uint32_t IDESC_S = make_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);
   constexpr uint32_t IDESC_PV = make_idesc_bf16(ATT_BQ, D, 0, 1);
+  static_assert(ATT_NQ * SLOT_COLS <= 512, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -80,18 +77,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* k_empty = k_full + STAGES;
   uint64_t* v_full = k_empty + STAGES;
   uint64_t* v_empty = v_full + STAGES;
-  uint64_t* s_full = v_empty + STAGES;
-  uint64_t* p_ready = s_full + 2;
-  uint64_t* o_full = p_ready + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* s_full = v_empty + STAGES;  // [slot*2 + buf]
+  uint64_t* p_ready = s_full + 4;       // [slot]
+  uint64_t* o_done = p_ready + 2;       // [slot]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2);
+  float* red = reinterpret_cast<float*>(smem + S::OFF_RED);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_pairs = gridDim.x;
-  const int pair = num_pairs - 1 - blockIdx.x;  // heavy (late) causal tiles first
+  const int pair = gridDim.x - 1 - blockIdx.x;  // heavy (late) causal tiles first
   const int head = blockIdx.y, b = blockIdx.z;
   const int q0 = pair * (ATT_NQ * ATT_BQ);
 
-  // number of KV steps per slot
   const int n_all = (p.seq_kv + ATT_BKV - 1) / ATT_BKV;
   int n_kv[ATT_NQ];
 #pragma unroll
@@ -103,32 +99,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   const int n_total = max(n_kv[0], n_kv[1]);
 
-  if (warp == 8 && lane == 0) {
+  if (warp == ATT_W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], ATT_BQ); mbar_init(&o_full[i], 1);
-    }
+    for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], ATT_GROUP); mbar_init(&o_done[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 9) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  if (warp == ATT_W_MMA) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp >= 8) {
-    reg_dec<40>();
-    if (warp == 8 && lane == 0) {
-      // ===================== TMA producer =====================
-      const int qc = p.q_col0 + head * p.q_head_stride;
-      const int kc = p.k_col0 + head * p.k_head_stride;
-      const int vc = p.v_col0 + head * p.v_head_stride;
-      int active = (n_kv[0] > 0) + (n_kv[1] > 0);
+  if (warp == ATT_W_TMA) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const int qc = head * p.q_head_stride, kc = head * p.k_head_stride, vc = head * p.v_head_stride;
+      const int active = (n_kv[0] > 0) + (n_kv[1] > 0);
       mbar_expect_tx(q_full, active * S::Q_BYTES);
 #pragma unroll
       for (int i = 0; i < ATT_NQ; ++i) {
@@ -153,163 +145,190 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                       j * ATT_BKV, b);
         if (++st == STAGES) { st = 0; ph ^= 1; }
       }
-    } else if (warp == 9) {
-      // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
-      const uint64_t dsc_q = make_smem_desc_sw128(smem_u32(smem + S::OFF_Q), 0, 1024);
-      const uint64_t dsc_k = make_smem_desc_sw128(smem_u32(smem + S::OFF_K), 0, 1024);
-      const uint64_t dsc_p = make_smem_desc_sw128(smem_u32(smem + S::OFF_P), 0, 1024);
-      const uint64_t dsc_v = make_smem_desc_sw128(smem_u32(smem + S::OFF_V), ATT_BKV * 128, 1024);  // MN-major
-      auto issue_S = [&](int slot, int st) {   // caller: inside elect_one()
-        const uint64_t da = dsc_q + uint64_t(slot) * (S::Q_BYTES >> 4), db = dsc_k + uint64_t(st) * (S::KV_BYTES >> 4);
+    }
+  } else if (warp == ATT_W_MMA) {
+    // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
+    const uint64_t dsc_q = make_smem_desc_sw128(smem_u32(smem + S::OFF_Q), 0, 1024);
+    const uint64_t dsc_k = make_smem_desc_sw128(smem_u32(smem + S::OFF_K), 0, 1024);
+    const uint64_t dsc_p = make_smem_desc_sw128(smem_u32(smem + S::OFF_P), 0, 1024);
+    const uint64_t dsc_v = make_smem_desc_sw128(smem_u32(smem + S::OFF_V), ATT_BKV * 128, 1024);  // MN-major
+    auto issue_S = [&](int slot, int buf, int st) {   // caller holds elect_one()
+      const uint64_t da = dsc_q + uint64_t(slot) * (S::Q_BYTES >> 4), db = dsc_k + uint64_t(st) * (S::KV_BYTES >> 4);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)
-          umma_bf16(tmem_base + TM_S + slot * ATT_BKV, da + (((kk / 4) * (ATT_BQ * 128) + (kk % 4) * 32) >> 4),
-                    db + (((kk / 4) * (ATT_BKV * 128) + (kk % 4) * 32) >> 4), IDESC_S, kk != 0);
-      };
-      auto issue_PV = [&](int slot, int st) {
-        const uint64_t da = dsc_p + uint64_t(slot) * (S::P_BYTES >> 4), db = dsc_v + uint64_t(st) * (S::KV_BYTES >> 4);
+      for (int kk = 0; kk < D / 16; ++kk)
+        umma_bf16(tmem_base + slot * SLOT_COLS + buf * ATT_BKV, da + (((kk / 4) * (ATT_BQ * 128) + (kk % 4) * 32) >> 4),
+                  db + (((kk / 4) * (ATT_BKV * 128) + (kk % 4) * 32) >> 4), IDESC_S, kk != 0);
+      umma_commit(&s_full[slot * 2 + buf]);
+    };
+    auto issue_PV = [&](int slot, int buf, int st, bool accumulate) {
+      const uint64_t da = dsc_p + uint64_t(slot * 2 + buf) * (S::P_BYTES >> 4), db = dsc_v + uint64_t(st) * (S::KV_BYTES >> 4);
 #pragma unroll
-        for (int kk = 0; kk < ATT_BKV / 16; ++kk)
-          umma_bf16(tmem_base + TM_O + slot * D, da + ((kk * 32) >> 4), db + ((kk * 2048) >> 4), IDESC_PV, kk != 0);
-      };
-      mbar_wait(q_full, 0);
-      int st = 0; uint32_t ph = 0;
-      if (n_total > 0) {
-        mbar_wait(&k_full[0], 0);
+      for (int kk = 0; kk < ATT_BKV / 16; ++kk)
+        umma_bf16(tmem_base + slot * SLOT_COLS + 2 * ATT_BKV, da + ((kk * 32) >> 4), db + ((kk * 2048) >> 4), IDESC_PV,
+                  (accumulate || kk != 0) ? 1u : 0u);
+      umma_commit(&o_done[slot]);
+    };
+    mbar_wait(q_full, 0);
+    // prologue: S(0) and S(1) of every active slot
+    for (int t = 0; t < 2 && t < n_total; ++t) {
+      mbar_wait(&k_full[t % STAGES], (t / STAGES) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        for (int i = 0; i < ATT_NQ; ++i)
+          if (t < n_kv[i]) issue_S(i, t & 1, t % STAGES);
+        umma_commit(&k_empty[t % STAGES]);
+      }
+      __syncwarp();
+    }
+    for (int j = 0; j < n_total; ++j) {
+      const int st = j % STAGES;
+      const uint32_t ph = (j / STAGES) & 1;
+      const int t2 = j + 2, st2 = t2 % STAGES;
+      const uint32_t ph2 = (t2 / STAGES) & 1;
+      bool v_waited = false, k_waited = false;
+      for (int i = 0; i < ATT_NQ; ++i) {
+        if (j >= n_kv[i]) continue;
+        mbar_wait(&p_ready[i], j & 1);
+        if (!v_waited) { mbar_wait(&v_full[st], ph); v_waited = true; }
+        const bool more = t2 < n_kv[i];
+        if (more && !k_waited) { mbar_wait(&k_full[st2], ph2); k_waited = true; }
         tc_fence_after();
         if (elect_one()) {
-          for (int i = 0; i < ATT_NQ; ++i)
-            if (n_kv[i] > 0) { issue_S(i, 0); umma_commit(&s_full[i]); }
-          umma_commit(&k_empty[0]);
+          issue_PV(i, j & 1, st, j > 0);
+          if (more) issue_S(i, j & 1, st2);   // S buffer (j & 1) was consumed by softmax step j
         }
         __syncwarp();
       }
-      for (int j = 0; j < n_total; ++j) {
-        int st1 = st + 1; uint32_t ph1 = ph;
-        if (st1 == STAGES) { st1 = 0; ph1 ^= 1; }
-        bool v_waited = false;
-        for (int i = 0; i < ATT_NQ; ++i) {
-          if (j >= n_kv[i]) continue;
-          mbar_wait(&p_ready[i], j & 1);
-          if (!v_waited) { mbar_wait(&v_full[st], ph); v_waited = true; }
-          const bool more = j + 1 < n_kv[i];
-          if (more) mbar_wait(&k_full[st1], ph1);
-          tc_fence_after();
-          if (elect_one()) {
-            issue_PV(i, st);
-            umma_commit(&o_full[i]);
-            if (more) { issue_S(i, st1); umma_commit(&s_full[i]); }
-          }
-          __syncwarp();
-        }
-        if (elect_one()) {
-          umma_commit(&v_empty[st]);
-          if (j + 1 < n_total) umma_commit(&k_empty[st1]);
-        }
-        __syncwarp();
-        st = st1; ph = ph1;
+      if (elect_one()) {
+        umma_commit(&v_empty[st]);
+        if (t2 < n_total) umma_commit(&k_empty[st2]);
       }
+      __syncwarp();
     }
   } else {
-    // ===================== softmax warpgroups =====================
-    reg_inc<216>();
-    const int slot = warp >> 2;
-    const int quad = warp & 3;
+    // ===================== softmax groups =====================
+    const int slot = warp >> 3;
+    const int gw = warp & 7;
+    const int quad = gw & 3, half = gw >> 2;
     const int r_in = quad * 32 + lane;            // row inside the tile == TMEM lane
     const int q_row = q0 + slot * ATT_BQ + r_in;  // position in the sequence
     const int n_mine = n_kv[slot];
-    const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16);
-    uint8_t* sP = smem + S::OFF_P + slot * S::P_BYTES + r_in * 128;
+    const uint32_t t_slot = tmem_base + (uint32_t(quad * 32) << 16) + slot * SLOT_COLS;
     const int sw = r_in & 7;
     const uint8_t* mrow = p.kv_mask ? p.kv_mask + int64_t(b) * p.seq_kv : nullptr;
+    float* red_mine = red + (slot * 2 + half) * ATT_BQ + r_in;
+    float* red_peer = red + (slot * 2 + (half ^ 1)) * ATT_BQ + r_in;
+    const int bar_id = 1 + slot;
 
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) o[d] = 0.f;
-
+    float m_ref = -INFINITY, l_part = 0.f;
     for (int j = 0; j < n_mine; ++j) {
-      mbar_wait(&s_full[slot], j & 1);
+      const int buf = j & 1;
+      mbar_wait(&s_full[slot * 2 + buf], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld32(t_lane + TM_S + slot * ATT_BKV, r0);
-      tmem_ld32(t_lane + TM_S + slot * ATT_BKV + 32, r1);
+      uint32_t s[32];
+      tmem_ld32(t_slot + buf * ATT_BKV + half * 32, s);
       tmem_ld_wait();
-      const int kv0 = j * ATT_BKV;
-      const bool need_mask = (p.causal && kv0 + ATT_BKV - 1 > q0 + slot * ATT_BQ) || (kv0 + ATT_BKV > p.seq_kv) || mrow;
+      const int c0 = j * ATT_BKV + half * 32;
+      const bool need_mask = (p.causal && j * ATT_BKV + ATT_BKV - 1 > q0 + slot * ATT_BQ) ||
+                             (j * ATT_BKV + ATT_BKV > p.seq_kv) || mrow;
       float mx = -INFINITY;
       if (!need_mask) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const float a = __uint_as_float(r0[c]) * p.scale_log2, bq = __uint_as_float(r1[c]) * p.scale_log2;
-          r0[c] = __float_as_uint(a); r1[c] = __float_as_uint(bq);
-          mx = fmaxf(mx, fmaxf(a, bq));
+          const float a = __uint_as_float(s[c]) * p.scale_log2;
+          s[c] = __float_as_uint(a);
+          mx = fmaxf(mx, a);
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          float s = __uint_as_float(c < 32 ? r0[c & 31] : r1[c & 31]) * p.scale_log2;
-          const int col = kv0 + c;
+        for (int c = 0; c < 32; ++c) {
+          const int col = c0 + c;
           bool keep = col < p.seq_kv && !(p.causal && col > q_row);
           if (keep && mrow) keep = mrow[col] != 0;
-          s = keep ? s : -INFINITY;
-          if (c < 32) r0[c & 31] = __float_as_uint(s); else r1[c & 31] = __float_as_uint(s);
-          mx = fmaxf(mx, s);
+          const float a = keep ? __uint_as_float(s[c]) * p.scale_log2 : -INFINITY;
+          s[c] = __float_as_uint(a);
+          mx = fmaxf(mx, a);
         }
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = ex2_approx_f(m_run - m_use);  // m_run == -inf -> 0
-      float sum = 0.f;
-      uint32_t pk[32];
+      // full-row max: exchange with the thread holding the other 32 columns of this row
+      *red_mine = mx;
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+      mx = fmaxf(mx, *red_peer);
+      // lazy reference update (identical decision in both threads of the row)
+      const bool raise = mx > m_ref + ATT_RESCALE_TAU;
+      const bool resc = raise && m_ref != -INFINITY;   // something was accumulated with the old reference
+      const float f = resc ? ex2_approx(m_ref - mx) : 1.f;
+      // TMEM ld/st are warp-collective (.sync.aligned): the whole warp takes the branch if ANY row needs it (factor 1 elsewhere)
+      if (j > 0 && __any_sync(0xffffffffu, resc)) {
+        mbar_wait(&o_done[slot], (j - 1) & 1);   // PV(j-1) must have landed in TMEM
+        tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 64; c += 2) {
-        const float a = ex2_approx_f(__uint_as_float(c < 32 ? r0[c & 31] : r1[c & 31]) - m_use);
-        const float bb = ex2_approx_f(__uint_as_float(c + 1 < 32 ? r0[(c + 1) & 31] : r1[(c + 1) & 31]) - m_use);
-        pk[c >> 1] = pack_bf16x2(a, bb);
-        // sum what the tensor core will actually see (bf16-rounded), keeps rows normalised
-        sum += bf16lo(pk[c >> 1]) + bf16hi(pk[c >> 1]);
-      }
+        for (int ch = 0; ch < D / 64; ++ch) {    // this thread's half of the O columns
+          uint32_t t[32];
+          const uint32_t addr = t_slot + 2 * ATT_BKV + (half * (D / 64) + ch) * 32;
+          tmem_ld32(addr, t);
+          tmem_ld_wait();
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint4 q4 = make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-        *reinterpret_cast<uint4*>(sP + ((ch ^ sw) << 4)) = q4;
+          for (int c = 0; c < 32; ++c) t[c] = __float_as_uint(__uint_as_float(t[c]) * f);
+          tmem_st32(addr, t);
+        }
+        tmem_st_wait();
       }
+      l_part *= f;
+      if (raise) m_ref = mx;
+      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+      uint32_t pk[16];
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        const float a = ex2_approx(__uint_as_float(s[c]) - m_use);
+        const float bq = ex2_approx(__uint_as_float(s[c + 1]) - m_use);
+        pk[c >> 1] = pack_bf16x2(a, bq);
+        l_part += bf16lo(pk[c >> 1]) + bf16hi(pk[c >> 1]);  // sum what the tensor core will see (bf16-rounded)
+      }
+      uint8_t* sP = smem + S::OFF_P + (slot * 2 + buf) * S::P_BYTES + r_in * 128;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        *reinterpret_cast<uint4*>(sP + (((half * 4 + ch) ^ sw) << 4)) =
+            make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      tc_fence_before();     // order our tcgen05.ld of S / O before the MMAs that overwrite them
+      tc_fence_before();     // order our tcgen05.ld/st before the MMAs that read / overwrite TMEM
       mbar_arrive(&p_ready[slot]);
-      l_run = l_run * alpha + sum;
-      m_run = m_new;
-
-      mbar_wait(&o_full[slot], j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int ch = 0; ch < D / 32; ++ch) {
-        uint32_t t[32];
-        tmem_ld32(t_lane + TM_O + slot * D + ch * 32, t);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) o[ch * 32 + c] = o[ch * 32 + c] * alpha + __uint_as_float(t[c]);
-      }
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");  // red[] may be rewritten next step
     }
-    // ---- epilogue: normalise, store O (bf16) and LSE (log2 domain)
-    if (n_mine > 0 && q_row < p.seq_q) {
+    // ---- epilogue: combine the two partial row sums, read O from TMEM, normalise, store O (bf16) and LSE (log2 domain)
+    if (n_mine > 0) {
+      *red_mine = l_part;
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+      const float l_run = l_part + *red_peer;
+      mbar_wait(&o_done[slot], (n_mine - 1) & 1);
+      tc_fence_after();
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      const bool row_ok = q_row < p.seq_q;
       __nv_bfloat16* op = p.o + (int64_t(b) * p.seq_q + q_row) * p.o_row_stride + int64_t(head) * p.o_head_stride;
 #pragma unroll
-      for (int d = 0; d < D; d += 8) {
-        float f[8];
+      for (int ch = 0; ch < D / 64; ++ch) {
+        const int cc = half * (D / 64) + ch;
+        uint32_t t[32];
+        tmem_ld32(t_slot + 2 * ATT_BKV + cc * 32, t);
+        tmem_ld_wait();
+        if (row_ok) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) f[t] = o[d + t] * inv;
-        *reinterpret_cast<uint4*>(op + d) = pack8(f);
+          for (int c = 0; c < 32; c += 8) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(t[c + e]) * inv;
+            *reinterpret_cast<uint4*>(op + cc * 32 + c) = pack8(f);
+          }
+        }
       }
-      p.lse[(int64_t(b) * p.nheads + head) * p.seq_q + q_row] = l_run > 0.f ? m_run + log2f(l_run) : INFINITY;
+      if (row_ok && half == 0)
+        p.lse[(int64_t(b) * p.nheads + head) * p.seq_q + q_row] = l_run > 0.f ? m_ref + log2f(l_run) : INFINITY;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == ATT_W_MMA) {
     tc_fence_after();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
@@ -369,7 +388,6 @@ extern "C" int fsb_sdpa_fwd(const void* q, const void* k, const void* v, void* o
   AttFwdParams p;
   p.o = (__nv_bfloat16*)o; p.lse = lse; p.kv_mask = kv_mask;
   p.o_row_stride = o_row_stride; p.o_head_stride = o_head_stride;
-  p.q_col0 = 0; p.k_col0 = 0; p.v_col0 = 0;
   p.q_head_stride = int(q_head_stride); p.k_head_stride = int(k_head_stride); p.v_head_stride = int(v_head_stride);
   p.seq_q = int(seq_q); p.seq_kv = int(seq_kv); p.nheads = nheads; p.batch = int(batch);
   p.causal = causal;
