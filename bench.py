@@ -33,6 +33,15 @@ WORKLOADS = {
     "gpt2-110m": dict(family="gpt2", vocab_size=50264, n_positions=1024, n_embd=768, n_layer=12, n_head=12, seq=1024,
                       per_gpu=32, micro=32, lr=1e-4, betas=(0.9, 0.999), wd=0.1, clip=0.0,
                       label="Wenzhong-GPT2-110M pretrain, seq 1024, batch 32/GPU (BASELINE configs[1])"),
+    "bert-base": dict(family="bert", variant="bert", vocab_size=21128, hidden_size=768, num_hidden_layers=12,
+                      num_attention_heads=12, intermediate_size=3072, hidden_act="gelu", seq=128, per_gpu=8, micro=8,
+                      lr=1e-4, betas=(0.9, 0.999), wd=0.1, clip=0.0,
+                      label="Erlangshen-BERT-base MLM, seq 128, batch 8 (BASELINE configs[0])"),
+    "megatronbert-1.3b": dict(family="bert", variant="megatron", vocab_size=21128, hidden_size=2048,
+                              num_hidden_layers=24, num_attention_heads=32, intermediate_size=8192, hidden_act="gelu",
+                              seq=512, per_gpu=128, micro=32, lr=1e-4, betas=(0.9, 0.999), wd=0.1, clip=1.0,
+                              label="Erlangshen-MegatronBERT-1.3B MLM+SOP pretrain, seq 512, batch 128/GPU, ZeRO-1 "
+                                    "(BASELINE configs[2])"),
     "ziya-llama-13b": dict(family="llama", vocab_size=39424, hidden_size=5120, num_hidden_layers=40,
                            num_attention_heads=40, seq=2048, per_gpu=32, micro=4, lr=1e-4, betas=(0.9, 0.95), wd=0.1,
                            clip=1.0, label="Ziya-LLaMA-13B pretrain, seq 2048, global batch 32/GPU, ZeRO-2 (BASELINE configs[3])"),
@@ -56,6 +65,10 @@ def flops_per_token(w):
         h, L, V, s = w["n_embd"], w["n_layer"], w["vocab_size"], w["seq"]
         n_mm = L * 12 * h * h + V * h
         attn = 4 * s * h * L / 2
+    elif w["family"] == "bert":
+        h, L, V, s, ff = w["hidden_size"], w["num_hidden_layers"], w["vocab_size"], w["seq"], w["intermediate_size"]
+        n_mm = L * (4 * h * h + 2 * h * ff) + h * h + V * h      # + MLM transform dense + tied decoder
+        attn = 4 * s * h * L                                      # bidirectional: full s x s
     else:
         h, L, V, s = w["hidden_size"], w["num_hidden_layers"], w["vocab_size"], w["seq"]
         ff = 256 * ((int(2 * h * 4 / 3) + 255) // 256)
@@ -118,8 +131,15 @@ def make_host_batches(w, n_pool, rank):
     g = torch.Generator().manual_seed(1234 + rank)
     out = []
     for _ in range(n_pool):
-        ids = torch.randint(0, w["vocab_size"] - 8, (w["micro"], w["seq"]), generator=g, dtype=torch.int64)
-        b = {"input_ids": ids.pin_memory(), "labels": ids.clone().pin_memory()}
+        ids = torch.randint(1, w["vocab_size"] - 8, (w["micro"], w["seq"]), generator=g, dtype=torch.int64)
+        if w["family"] == "bert":   # MLM: labels = -100 except a Bernoulli(0.15) subset; C3 adds NSP labels
+            sel = torch.rand(ids.shape, generator=g) < 0.15
+            b = {"input_ids": ids.pin_memory(), "labels": torch.where(sel, ids, torch.full_like(ids, -100)).pin_memory(),
+                 "token_type_ids": torch.zeros_like(ids).pin_memory()}
+            if w["variant"] == "megatron":
+                b["next_sentence_label"] = torch.randint(0, 2, (w["micro"],), generator=g, dtype=torch.int64).pin_memory()
+        else:
+            b = {"input_ids": ids.pin_memory(), "labels": ids.clone().pin_memory()}
         out.append(b)
     return out
 
@@ -132,6 +152,15 @@ def build_model(w, device, world):
                               n_layer=w["n_layer"], n_head=w["n_head"], layer_norm_epsilon=1e-5, initializer_range=0.02,
                               resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0, activation_function="gelu_new")
         return GPT2LMHeadModel(cfg, device=device, world_size=world)
+    if w["family"] == "bert":
+        from fsb200.models.bert import BertForMaskedLM, MegatronBertForPreTraining
+        cfg = SimpleNamespace(vocab_size=w["vocab_size"], hidden_size=w["hidden_size"],
+                              num_hidden_layers=w["num_hidden_layers"], num_attention_heads=w["num_attention_heads"],
+                              intermediate_size=w["intermediate_size"], hidden_act=w["hidden_act"],
+                              max_position_embeddings=512, type_vocab_size=2, layer_norm_eps=1e-12,
+                              hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, initializer_range=0.02)
+        cls = MegatronBertForPreTraining if w["variant"] == "megatron" else BertForMaskedLM
+        return cls(cfg, device=device, world_size=world)
     from fsb200.models.llama import LlamaForCausalLM
     cfg = SimpleNamespace(vocab_size=w["vocab_size"], hidden_size=w["hidden_size"],
                           num_hidden_layers=w["num_hidden_layers"], num_attention_heads=w["num_attention_heads"],
@@ -177,6 +206,24 @@ def cpu_reference_tokens_per_s(w, budget_s=20.0):
             loss.backward()
             opt.step()
         kind, sample, scale = "reference", f"transformers GPT2LMHeadModel fp32 + torch AdamW, batch {B} x seq {S}", 1.0
+    elif w["family"] == "bert":
+        import hf_oracle as H
+        cfg = dict(vocab_size=w["vocab_size"], hidden_size=w["hidden_size"], num_hidden_layers=w["num_hidden_layers"],
+                   num_attention_heads=w["num_attention_heads"], intermediate_size=w["intermediate_size"],
+                   max_position_embeddings=512, type_vocab_size=2)
+        meg = w["variant"] == "megatron"
+        model = (H.build_megatron_bert if meg else H.build_bert)(cfg, bf16_exact=False)
+        opt = torch.optim.AdamW(H.wenzhong_param_groups(model.named_parameters(), w["wd"]), lr=w["lr"])
+        B, S = (1 if meg else 8), w["seq"]
+        batch = H.make_mlm_batch(w["vocab_size"], B, S, nsp=meg)
+
+        def one():
+            loss = model(**batch).loss
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+        kind, scale = "reference", 1.0
+        sample = f"transformers {type(model).__name__} fp32 + torch AdamW, batch {B} x seq {S}"
     else:
         import llama_oracle as O
         Lr = 1  # one full-width layer + head, extrapolated linearly in L (full size does not fit host RAM)
