@@ -60,6 +60,12 @@ SIGNATURES = {
     "fsb_sumsq_workspace_bytes": (c_size, []),
     "fsb_sumsq": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_int, c_void_p, c_size, c_void_p]),
     "fsb_clip_coef": (c_int, [c_void_p, c_f32, c_void_p, c_void_p, c_void_p]),
+    "fsb_scaled_masked_softmax_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32,
+                                              c_void_p]),
+    "fsb_scaled_masked_softmax_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_f32, c_void_p]),
+    "fsb_scaled_upper_triang_masked_softmax_fwd": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_f32, c_void_p]),
+    "fsb_scaled_upper_triang_masked_softmax_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_f32, c_void_p]),
+    "fsb_softmax_get_batch_per_block": (c_int, [c_i64, c_i64, c_i64, c_i64]),
     "fsb_sdpa_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int,
                              c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_void_p, c_void_p]),
     "fsb_sdpa_bwd": (c_int, [c_void_p] * 10 + [c_i64, c_i64, c_i64, c_int, c_int] + [c_i64] * 16 +

@@ -154,6 +154,26 @@ int fsb_sumsq(const void* x, int dtype, int64_t n, float* out, int accumulate, v
               fsb_stream_t stream);
 int fsb_clip_coef(const float* sumsq, float max_norm, float* coef, float* norm_out, fsb_stream_t stream);
 
+/* ---- the reference's own two CUDA ops (legacy non-flash attention path) -------------------------------------
+ * scaled_masked_softmax_cuda.{forward, backward, get_batch_per_block}  fused_kernels/scaled_masked_softmax.cpp:70-83
+ *   forward : y = softmax(mask == 1 ? -10000 : scale * x) over sk; x, y bf16 [batches, attn_heads, sq, sk];
+ *             mask uint8 [mask_batches (1 or batches), 1, sq, sk] or NULL (scaled_masked_softmax.h:117-238).
+ *   backward: dy <- scale * (dy*y - y*sum(dy*y)) IN PLACE (scaled_masked_softmax_cuda.cu:95-105); rows = b*np*sq.
+ * scaled_upper_triang_masked_softmax_cuda.{forward, backward}          scaled_upper_triang_masked_softmax.cpp:62-70
+ *   causal variant on [attn_batches, seq_len, seq_len]; zeros above the diagonal.
+ * sk % 8 == 0, sk <= 4096 (the reference asserts sk <= 2048 and silently skips unsupported sizes, .h:448; here any
+ * violation is an error). fsb_softmax_get_batch_per_block reproduces the reference's launch-geometry helper that
+ * layers/fused_softmax.py:163-170 uses to gate the fused path. */
+int fsb_scaled_masked_softmax_fwd(const void* x, const uint8_t* mask, void* y, int64_t batches, int64_t attn_heads,
+                                  int64_t sq, int64_t sk, int64_t mask_batches, float scale, fsb_stream_t stream);
+int fsb_scaled_masked_softmax_bwd(void* dy_inplace, const void* y, int64_t rows, int64_t sk, float scale,
+                                  fsb_stream_t stream);
+int fsb_scaled_upper_triang_masked_softmax_fwd(const void* x, void* y, int64_t attn_batches, int64_t seq_len,
+                                               float scale, fsb_stream_t stream);
+int fsb_scaled_upper_triang_masked_softmax_bwd(void* dy_inplace, const void* y, int64_t attn_batches, int64_t seq_len,
+                                               float scale, fsb_stream_t stream);
+int fsb_softmax_get_batch_per_block(int64_t sq, int64_t sk, int64_t batches, int64_t attn_heads);
+
 /* ---- fused scaled-dot-product attention (tcgen05, flash-style online softmax) ------------------------------
  * Replaces ParallelSelfAttention.flash_attention (fengshen/models/megatron/layers/transformer.py:410-456; 3P
  * flash_attn_cuda.fwd/bwd, layers/flash_attention.py:31-47,81-101) and the legacy baddbmm -> FusedScaleMaskSoftmax ->
