@@ -93,6 +93,7 @@ struct AttBwdSmem {
   static constexpr int OFF_BAR = OFF_STATS + 2 * 2 * 64 * 4;
   static constexpr int NBAR = 1 + 2 * STAGES + 2 + 2 + 1;  // big_full, sml_full[S], sml_empty[S], s_full[2], t_ready[2], done
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into on sm_100");
 };
 
 // ================================================================================================ dQ kernel

@@ -39,11 +39,12 @@ struct AttFwdSmem {
   static constexpr int OFF_K = OFF_Q + ATT_NQ * Q_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * KV_BYTES;
   static constexpr int OFF_P = OFF_V + STAGES * KV_BYTES;  // [slot][buf]
-  static constexpr int OFF_RED = OFF_P + ATT_NQ * 2 * P_BYTES;  // float [slot][half][128]: row max / row sum exchange
-  static constexpr int OFF_BAR = OFF_RED + ATT_NQ * 2 * ATT_BQ * 4;
-  // q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2][2], p_ready[2], o_done[2]
-  static constexpr int NBAR = 1 + 4 * STAGES + 8;
+  static constexpr int OFF_RED = OFF_P + ATT_NQ * 2 * P_BYTES;  // bf16 [slot][half][128]: row-max exchange (1 KB)
+  static constexpr int OFF_BAR = OFF_RED + ATT_NQ * 2 * ATT_BQ * 2;
+  // q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2][2], p_ready[2][2], o_done[2]
+  static constexpr int NBAR = 1 + 4 * STAGES + 10;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into on sm_100");
 };
 
 struct AttFwdParams {
@@ -78,10 +79,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* v_full = k_empty + STAGES;
   uint64_t* v_empty = v_full + STAGES;
   uint64_t* s_full = v_empty + STAGES;  // [slot*2 + buf]
-  uint64_t* p_ready = s_full + 4;       // [slot]
-  uint64_t* o_done = p_ready + 2;       // [slot]
+  uint64_t* p_ready = s_full + 4;       // [slot*2 + buf]: per P buffer, because a softmax group may run one step ahead
+  uint64_t* o_done = p_ready + 4;       // [slot]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2);
-  float* red = reinterpret_cast<float*>(smem + S::OFF_RED);
+  __nv_bfloat16* red = reinterpret_cast<__nv_bfloat16*>(smem + S::OFF_RED);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = gridDim.x - 1 - blockIdx.x;  // heavy (late) causal tiles first
@@ -107,7 +108,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], ATT_GROUP); mbar_init(&o_done[i], 1); }
+    for (int i = 0; i < 4; ++i) mbar_init(&p_ready[i], ATT_GROUP);
+    for (int i = 0; i < 2; ++i) mbar_init(&o_done[i], 1);
     fence_barrier_init();
   }
   if (warp == ATT_W_MMA) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
@@ -188,7 +190,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       bool v_waited = false, k_waited = false;
       for (int i = 0; i < ATT_NQ; ++i) {
         if (j >= n_kv[i]) continue;
-        mbar_wait(&p_ready[i], j & 1);
+        mbar_wait(&p_ready[i * 2 + (j & 1)], (j >> 1) & 1);
         if (!v_waited) { mbar_wait(&v_full[st], ph); v_waited = true; }
         const bool more = t2 < n_kv[i];
         if (more && !k_waited) { mbar_wait(&k_full[st2], ph2); k_waited = true; }
@@ -216,8 +218,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t t_slot = tmem_base + (uint32_t(quad * 32) << 16) + slot * SLOT_COLS;
     const int sw = r_in & 7;
     const uint8_t* mrow = p.kv_mask ? p.kv_mask + int64_t(b) * p.seq_kv : nullptr;
-    float* red_mine = red + (slot * 2 + half) * ATT_BQ + r_in;
-    float* red_peer = red + (slot * 2 + (half ^ 1)) * ATT_BQ + r_in;
+    __nv_bfloat16* red_mine = red + (slot * 2 + half) * ATT_BQ + r_in;
+    __nv_bfloat16* red_peer = red + (slot * 2 + (half ^ 1)) * ATT_BQ + r_in;
     const int bar_id = 1 + slot;
 
     float m_ref = -INFINITY, l_part = 0.f;
@@ -251,9 +253,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       // full-row max: exchange with the thread holding the other 32 columns of this row
-      *red_mine = mx;
+      // the exponent reference need not be the exact max: both threads use max(bf16(own), bf16(peer)) — identical on both
+      // sides, at most 2^-8 relative below the true max (probabilities stay < 2^(tau+1))
+      *red_mine = __float2bfloat16(mx);
       asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-      mx = fmaxf(mx, *red_peer);
+      mx = fmaxf(__bfloat162float(*red_mine), __bfloat162float(*red_peer));
       // lazy reference update (identical decision in both threads of the row)
       const bool raise = mx > m_ref + ATT_RESCALE_TAU;
       const bool resc = raise && m_ref != -INFINITY;   // something was accumulated with the old reference
@@ -292,16 +296,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();     // order our tcgen05.ld/st before the MMAs that read / overwrite TMEM
-      mbar_arrive(&p_ready[slot]);
+      mbar_arrive(&p_ready[slot * 2 + buf]);
       asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");  // red[] may be rewritten next step
     }
     // ---- epilogue: combine the two partial row sums, read O from TMEM, normalise, store O (bf16) and LSE (log2 domain)
     if (n_mine > 0) {
-      *red_mine = l_part;
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-      const float l_run = l_part + *red_peer;
-      mbar_wait(&o_done[slot], (n_mine - 1) & 1);
+      mbar_wait(&o_done[slot], (n_mine - 1) & 1);   // all PVs done: this slot's P buffers are free -> fp32 scratch
       tc_fence_after();
+      float* lsum = reinterpret_cast<float*>(smem + S::OFF_P + slot * 2 * S::P_BYTES);   // [half][128]
+      lsum[half * ATT_BQ + r_in] = l_part;
+      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+      const float l_run = l_part + lsum[(half ^ 1) * ATT_BQ + r_in];
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       const bool row_ok = q_row < p.seq_q;
       __nv_bfloat16* op = p.o + (int64_t(b) * p.seq_q + q_row) * p.o_row_stride + int64_t(head) * p.o_head_stride;

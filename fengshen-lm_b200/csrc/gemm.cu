@@ -45,6 +45,7 @@ struct GemmSmem {
   static constexpr int BAR_OFFSET = STORE_OFFSET + 2 * STORE_BYTES;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024 /*align slack*/;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into on sm_100");
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float x) {
