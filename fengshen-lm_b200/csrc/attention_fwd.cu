@@ -58,6 +58,14 @@ struct AttFwdParams {
   float scale_log2;  // softmax scale * log2(e)
 };
 
+// Optional cycle trace of one CTA (development aid; compiled in only with -DFSB_ATTN_TRACE)
+#ifdef FSB_ATTN_TRACE
+__device__ long long g_fwd_trace[2][64][8];
+#define FTRACE(role, step, k) do { if (ftrace_on && (step) < 64) g_fwd_trace[role][step][k] = clock64(); } while (0)
+#else
+#define FTRACE(role, step, k) do { } while (0)
+#endif
+
 template <int D>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -99,6 +107,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     else n_kv[i] = n_all;
   }
   const int n_total = max(n_kv[0], n_kv[1]);
+#ifdef FSB_ATTN_TRACE
+  const bool ftrace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
+                         (warp == 8 || warp == ATT_W_MMA);   // slot-1 math warp (most steps) and the MMA warp
+#endif
 
   if (warp == ATT_W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
@@ -190,16 +202,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       bool v_waited = false, k_waited = false;
       for (int i = 0; i < ATT_NQ; ++i) {
         if (j >= n_kv[i]) continue;
+        if (i == 1) FTRACE(1, j, 0);
         mbar_wait(&p_ready[i * 2 + (j & 1)], (j >> 1) & 1);
+        if (i == 1) FTRACE(1, j, 1);
         if (!v_waited) { mbar_wait(&v_full[st], ph); v_waited = true; }
         const bool more = t2 < n_kv[i];
         if (more && !k_waited) { mbar_wait(&k_full[st2], ph2); k_waited = true; }
         tc_fence_after();
+        if (i == 1) FTRACE(1, j, 2);
         if (elect_one()) {
           issue_PV(i, j & 1, st, j > 0);
           if (more) issue_S(i, j & 1, st2);   // S buffer (j & 1) was consumed by softmax step j
         }
         __syncwarp();
+        if (i == 1) FTRACE(1, j, 3);
       }
       if (elect_one()) {
         umma_commit(&v_empty[st]);
@@ -225,8 +241,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     float m_ref = -INFINITY, l_part = 0.f;
     for (int j = 0; j < n_mine; ++j) {
       const int buf = j & 1;
+      FTRACE(0, j, 0);
       mbar_wait(&s_full[slot * 2 + buf], (j >> 1) & 1);
       tc_fence_after();
+      FTRACE(0, j, 1);
       uint32_t s[32];
       tmem_ld32(t_slot + buf * ATT_BKV + half * 32, s);
       tmem_ld_wait();
@@ -255,8 +273,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // full-row max: exchange with the thread holding the other 32 columns of this row
       // the exponent reference need not be the exact max: both threads use max(bf16(own), bf16(peer)) — identical on both
       // sides, at most 2^-8 relative below the true max (probabilities stay < 2^(tau+1))
+      FTRACE(0, j, 2);
       *red_mine = __float2bfloat16(mx);
       asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+      FTRACE(0, j, 3);
       mx = fmaxf(__bfloat162float(*red_mine), __bfloat162float(*red_peer));
       // lazy reference update (identical decision in both threads of the row)
       const bool raise = mx > m_ref + ATT_RESCALE_TAU;
@@ -278,6 +298,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         tmem_st_wait();
       }
+      FTRACE(0, j, 4);
       l_part *= f;
       if (raise) m_ref = mx;
       const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
@@ -287,8 +308,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float a = ex2_approx(__uint_as_float(s[c]) - m_use);
         const float bq = ex2_approx(__uint_as_float(s[c + 1]) - m_use);
         pk[c >> 1] = pack_bf16x2(a, bq);
-        l_part += bf16lo(pk[c >> 1]) + bf16hi(pk[c >> 1]);  // sum what the tensor core will see (bf16-rounded)
+        l_part += a + bq;   // fp32 sum of the unrounded probabilities (keeps LSE exact to fp32)
       }
+      FTRACE(0, j, 5);
       uint8_t* sP = smem + S::OFF_P + (slot * 2 + buf) * S::P_BYTES + r_in * 128;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch)
@@ -297,7 +319,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();     // order our tcgen05.ld/st before the MMAs that read / overwrite TMEM
       mbar_arrive(&p_ready[slot * 2 + buf]);
+      FTRACE(0, j, 6);
       asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");  // red[] may be rewritten next step
+      FTRACE(0, j, 7);
     }
     // ---- epilogue: combine the two partial row sums, read O from TMEM, normalise, store O (bf16) and LSE (log2 domain)
     if (n_mine > 0) {
@@ -371,6 +395,12 @@ static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const C
 }  // namespace fsb
 
 using namespace fsb;
+
+#ifdef FSB_ATTN_TRACE
+extern "C" int fsb_debug_attn_fwd_trace(long long* host_out /* [2][64][8] */) {
+  return cudaMemcpyFromSymbol(host_out, g_fwd_trace, sizeof(long long) * 2 * 64 * 8) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int fsb_sdpa_fwd(const void* q, const void* k, const void* v, void* o, float* lse, int64_t batch,
                             int64_t seq_q, int64_t seq_kv, int nheads, int head_dim, int64_t q_row_stride,

@@ -1,0 +1,45 @@
+"""Dev tool: build a traced copy of libfsb200 (-DFSB_ATTN_TRACE), run the forward kernel once, print per-step cycle deltas
+of CTA (0,0,0): softmax warp 8 (slot 1) and the MMA warp."""
+import ctypes
+import math
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+csrc = os.path.join(ROOT, "fengshen-lm_b200", "csrc")
+out = "/tmp/libfsb200_trace.so"
+srcs = [os.path.join(csrc, f) for f in
+        "host_common.cu gemm.cu norm.cu elementwise.cu loss_optim.cu attention_fwd.cu attention_bwd.cu softmax.cu".split()]
+subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DFSB_ATTN_TRACE",
+                "--compiler-options", "-fPIC", "-shared", "-o", out, "-cudart", "static"] + srcs, check=True)
+sys.path.insert(0, os.path.join(ROOT, "fengshen-lm_b200"))
+from fsb200 import lib  # noqa: E402
+lib.LIB_PATH = out
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+from fsb200 import ops  # noqa: E402
+
+B, S, H, D = (int(x) for x in sys.argv[1:5]) if len(sys.argv) > 4 else (8, 1024, 12, 64)
+qkv = torch.randn(B, S, 3, H, D, device="cuda", dtype=torch.bfloat16)
+q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+for _ in range(2):
+    o, lse = ops.sdpa_fwd(q, k, v, 1 / math.sqrt(D), True)
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * (2 * 64 * 8))()
+fn = lib.load().fsb_debug_attn_fwd_trace
+fn.argtypes = [ctypes.c_void_p]
+fn.restype = ctypes.c_int
+assert fn(buf) == 0
+t = np.array(buf, dtype=np.int64).reshape(2, 64, 8)
+n = min(S // 64, 64)
+base = t[0, 0, 0]
+print("softmax warp8: step | wait_s  ld+max  bar1  rescale  exp  stP+arrive  bar2 | step total")
+for j in range(n):
+    r = t[0, j]
+    nxt = t[0, j + 1, 0] if j + 1 < n else r[7]
+    print(f"{j:3d} | " + " ".join(f"{r[i+1]-r[i]:6d}" for i in range(7)) + f" | {nxt - r[0]:6d}   t0={r[0]-base}")
+print("mma warp (slot 1): step | wait_p  wait_kv  issue | total")
+for j in range(n):
+    r = t[1, j]
+    print(f"{j:3d} | {r[1]-r[0]:6d} {r[2]-r[1]:6d} {r[3]-r[2]:6d} | {r[3]-r[0]:6d}   t0={r[0]-base}")
