@@ -5,11 +5,12 @@
 // without the three repacking copies of q/k/v (transformer.py:419-429): Q, K, V are read straight out of the packed
 // QKV projection output through TMA tensor maps (any row/head stride), O is written in [token, head*dim] layout.
 //
-// CTA = one (batch, head, pair of 128-row Q tiles), 18 warps:
-//   warps 0-7 / 8-15 : softmax group of Q tile 0 / 1. TMEM lane == query row; the two threads of a row (warps w, w+4 of
-//                      the group share a lane quadrant) take 32 of the 64 key columns of a step each.
-//   warp 16          : TMA producer (Q once; K and V tiles through multi-stage rings)
-//   warp 17          : tcgen05.mma issuer: S_i(j) = Q_i K_j^T (128 x 64 x D), O_i += P_i(j) V_j (128 x D x 64)
+// CTA = one (batch, head, pair of 128-row Q tiles), 10 warps:
+//   warps 0-3 / 4-7 : softmax group of Q tile 0 / 1. TMEM lane == query row == thread: a thread owns the 64 scores of its
+//                     row for the step, so row max / row sum need no cross-thread exchange; S(j+1) is prefetched from
+//                     TMEM into a second register set while the exponentials of step j run.
+//   warp 8          : TMA producer (Q once; K and V tiles through multi-stage rings)
+//   warp 9          : tcgen05.mma issuer: S_i(j) = Q_i K_j^T (128 x 64 x D), O_i += P_i(j) V_j (128 x D x 64)
 // S is double-buffered in TMEM and P in shared memory, so the tensor core runs S(j+1)/S(j+2) while the softmax group
 // works on step j; the two Q tiles interleave on top of that.
 // O ACCUMULATES IN TMEM across the whole key loop. The running max used as exponent reference (m_ref) is only raised
@@ -24,9 +25,9 @@ namespace fsb {
 constexpr int ATT_BQ = 128;   // rows per Q tile (= TMEM lanes)
 constexpr int ATT_NQ = 2;     // Q tiles per CTA
 constexpr int ATT_BKV = 64;   // keys per inner step
-constexpr int ATT_GROUP = 256;                       // softmax threads per Q tile
-constexpr int ATT_THREADS = ATT_NQ * ATT_GROUP + 64; // + TMA warp + MMA warp
-constexpr int ATT_W_TMA = 16, ATT_W_MMA = 17;
+constexpr int ATT_GROUP = 128;                       // softmax threads per Q tile (one per row)
+constexpr int ATT_THREADS = ATT_NQ * ATT_GROUP + 128; // + warpgroup 2: TMA warp, MMA warp, two idle warps (setmaxnreg donors)
+constexpr int ATT_W_TMA = 8, ATT_W_MMA = 9;
 constexpr float ATT_RESCALE_TAU = 8.0f;              // log2 units
 
 template <int D>
@@ -39,8 +40,7 @@ struct AttFwdSmem {
   static constexpr int OFF_K = OFF_Q + ATT_NQ * Q_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * KV_BYTES;
   static constexpr int OFF_P = OFF_V + STAGES * KV_BYTES;  // [slot][buf]
-  static constexpr int OFF_RED = OFF_P + ATT_NQ * 2 * P_BYTES;  // bf16 [slot][half][128]: row-max exchange (1 KB)
-  static constexpr int OFF_BAR = OFF_RED + ATT_NQ * 2 * ATT_BQ * 2;
+  static constexpr int OFF_BAR = OFF_P + ATT_NQ * 2 * P_BYTES;
   // q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2][2], p_ready[2][2], o_done[2]
   static constexpr int NBAR = 1 + 4 * STAGES + 10;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
@@ -90,7 +90,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_ready = s_full + 4;       // [slot*2 + buf]: per P buffer, because a softmax group may run one step ahead
   uint64_t* o_done = p_ready + 4;       // [slot]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2);
-  __nv_bfloat16* red = reinterpret_cast<__nv_bfloat16*>(smem + S::OFF_RED);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pair = gridDim.x - 1 - blockIdx.x;  // heavy (late) causal tiles first
@@ -109,7 +108,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int n_total = max(n_kv[0], n_kv[1]);
 #ifdef FSB_ATTN_TRACE
   const bool ftrace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
-                         (warp == 8 || warp == ATT_W_MMA);   // slot-1 math warp (most steps) and the MMA warp
+                         (warp == 4 || warp == ATT_W_MMA);   // slot-1 math warp (most steps) and the MMA warp
 #endif
 
   if (warp == ATT_W_TMA && lane == 0) {
@@ -130,8 +129,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == ATT_W_TMA) {
+  // register split: 256 softmax threads * 216 + 128 (TMA / MMA / idle) * 72 = 384 * 168
+  if (warp > ATT_W_MMA) {
+    reg_dec<72>();   // idle donor warps
+  } else if (warp == ATT_W_TMA) {
     // ===================== TMA producer =====================
+    reg_dec<72>();
     if (lane == 0) {
       const int qc = head * p.q_head_stride, kc = head * p.k_head_stride, vc = head * p.v_head_stride;
       const int active = (n_kv[0] > 0) + (n_kv[1] > 0);
@@ -162,6 +165,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == ATT_W_MMA) {
     // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
+    reg_dec<72>();
     const uint64_t dsc_q = make_smem_desc_sw128(smem_u32(smem + S::OFF_Q), 0, 1024);
     const uint64_t dsc_k = make_smem_desc_sw128(smem_u32(smem + S::OFF_K), 0, 1024);
     const uint64_t dsc_p = make_smem_desc_sw128(smem_u32(smem + S::OFF_P), 0, 1024);
@@ -224,72 +228,65 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       __syncwarp();
     }
   } else {
-    // ===================== softmax groups =====================
-    const int slot = warp >> 3;
-    const int gw = warp & 7;
-    const int quad = gw & 3, half = gw >> 2;
+    // ===================== softmax groups: one thread per query row =====================
+    reg_inc<216>();
+    const int slot = warp >> 2;
+    const int quad = warp & 3;                    // TMEM lane quadrant this warp may access (= warp id % 4)
     const int r_in = quad * 32 + lane;            // row inside the tile == TMEM lane
     const int q_row = q0 + slot * ATT_BQ + r_in;  // position in the sequence
     const int n_mine = n_kv[slot];
     const uint32_t t_slot = tmem_base + (uint32_t(quad * 32) << 16) + slot * SLOT_COLS;
     const int sw = r_in & 7;
     const uint8_t* mrow = p.kv_mask ? p.kv_mask + int64_t(b) * p.seq_kv : nullptr;
-    __nv_bfloat16* red_mine = red + (slot * 2 + half) * ATT_BQ + r_in;
-    __nv_bfloat16* red_peer = red + (slot * 2 + (half ^ 1)) * ATT_BQ + r_in;
-    const int bar_id = 1 + slot;
+    const float sc = p.scale_log2;
 
-    float m_ref = -INFINITY, l_part = 0.f;
-    for (int j = 0; j < n_mine; ++j) {
+    float m_ref = -INFINITY;                      // exponent reference, scaled log2 domain
+    float l0 = 0.f, l1 = 0.f;                     // two partial row sums (shorter FADD chains)
+    uint32_t sa[64], sb[64];                      // S(j) and the prefetched S(j+1), raw fp32 scores
+
+    auto load_s = [&](int j, uint32_t (&dst)[64]) {   // asynchronous: tmem_ld_wait() before dst is read
+      mbar_wait(&s_full[slot * 2 + (j & 1)], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t a = t_slot + (j & 1) * ATT_BKV;
+      tmem_ld32_at<0>(a, dst);
+      tmem_ld32_at<32>(a + 32, dst);
+    };
+    auto step = [&](int j, uint32_t (&cur)[64], uint32_t (&nxt)[64]) {
       const int buf = j & 1;
       FTRACE(0, j, 0);
-      mbar_wait(&s_full[slot * 2 + buf], (j >> 1) & 1);
-      tc_fence_after();
+      tmem_ld_wait();                             // S(j) is in cur[]
       FTRACE(0, j, 1);
-      uint32_t s[32];
-      tmem_ld32(t_slot + buf * ATT_BKV + half * 32, s);
-      tmem_ld_wait();
-      const int c0 = j * ATT_BKV + half * 32;
-      const bool need_mask = (p.causal && j * ATT_BKV + ATT_BKV - 1 > q0 + slot * ATT_BQ) ||
-                             (j * ATT_BKV + ATT_BKV > p.seq_kv) || mrow;
-      float mx = -INFINITY;
-      if (!need_mask) {
+      const int c0 = j * ATT_BKV;
+      const bool need_mask = (p.causal && c0 + ATT_BKV - 1 > q0 + slot * ATT_BQ) || (c0 + ATT_BKV > p.seq_kv) || mrow;
+      if (need_mask) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float a = __uint_as_float(s[c]) * p.scale_log2;
-          s[c] = __float_as_uint(a);
-          mx = fmaxf(mx, a);
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < 64; ++c) {
           const int col = c0 + c;
           bool keep = col < p.seq_kv && !(p.causal && col > q_row);
           if (keep && mrow) keep = mrow[col] != 0;
-          const float a = keep ? __uint_as_float(s[c]) * p.scale_log2 : -INFINITY;
-          s[c] = __float_as_uint(a);
-          mx = fmaxf(mx, a);
+          if (!keep) cur[c] = 0xff800000u;        // -inf
         }
       }
-      // full-row max: exchange with the thread holding the other 32 columns of this row
-      // the exponent reference need not be the exact max: both threads use max(bf16(own), bf16(peer)) — identical on both
-      // sides, at most 2^-8 relative below the true max (probabilities stay < 2^(tau+1))
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 64; c += 4) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(cur[c + e]));
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sc;   // scale > 0 (checked on the host)
       FTRACE(0, j, 2);
-      *red_mine = __float2bfloat16(mx);
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-      FTRACE(0, j, 3);
-      mx = fmaxf(__bfloat162float(*red_mine), __bfloat162float(*red_peer));
-      // lazy reference update (identical decision in both threads of the row)
+      // lazy reference update: raise m_ref only when the row max outgrew it by more than 2^tau
       const bool raise = mx > m_ref + ATT_RESCALE_TAU;
       const bool resc = raise && m_ref != -INFINITY;   // something was accumulated with the old reference
       const float f = resc ? ex2_approx(m_ref - mx) : 1.f;
       // TMEM ld/st are warp-collective (.sync.aligned): the whole warp takes the branch if ANY row needs it (factor 1 elsewhere)
       if (j > 0 && __any_sync(0xffffffffu, resc)) {
-        mbar_wait(&o_done[slot], (j - 1) & 1);   // PV(j-1) must have landed in TMEM
+        mbar_wait(&o_done[slot], (j - 1) & 1);    // PV(j-1) must have landed in TMEM
         tc_fence_after();
 #pragma unroll
-        for (int ch = 0; ch < D / 64; ++ch) {    // this thread's half of the O columns
+        for (int ch = 0; ch < D / 32; ++ch) {
           uint32_t t[32];
-          const uint32_t addr = t_slot + 2 * ATT_BKV + (half * (D / 64) + ch) * 32;
+          const uint32_t addr = t_slot + 2 * ATT_BKV + ch * 32;
           tmem_ld32(addr, t);
           tmem_ld_wait();
 #pragma unroll
@@ -298,45 +295,47 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         tmem_st_wait();
       }
-      FTRACE(0, j, 4);
-      l_part *= f;
+      l0 *= f; l1 *= f;
       if (raise) m_ref = mx;
-      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-      uint32_t pk[16];
-#pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        const float a = ex2_approx(__uint_as_float(s[c]) - m_use);
-        const float bq = ex2_approx(__uint_as_float(s[c + 1]) - m_use);
-        pk[c >> 1] = pack_bf16x2(a, bq);
-        l_part += a + bq;   // fp32 sum of the unrounded probabilities (keeps LSE exact to fp32)
-      }
-      FTRACE(0, j, 5);
+      const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
+      FTRACE(0, j, 3);
+      // prefetch S(j+1) into the other register set while this step's exponentials run
+      if (j + 1 < n_mine) load_s(j + 1, nxt);
+      FTRACE(0, j, 4);
       uint8_t* sP = smem + S::OFF_P + (slot * 2 + buf) * S::P_BYTES + r_in * 128;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
-        *reinterpret_cast<uint4*>(sP + (((half * 4 + ch) ^ sw) << 4)) =
-            make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+      for (int ch = 0; ch < 8; ++ch) {            // 8 keys -> one 16-byte chunk of the 128B-swizzled P row
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = ex2_approx(fmaf(__uint_as_float(cur[ch * 8 + 2 * e]), sc, neg_m));
+          const float bq = ex2_approx(fmaf(__uint_as_float(cur[ch * 8 + 2 * e + 1]), sc, neg_m));
+          pk[e] = pack_bf16x2(a, bq);
+          l0 += a; l1 += bq;                      // fp32 sums of the unrounded probabilities (LSE exact to fp32)
+        }
+        *reinterpret_cast<uint4*>(sP + ((ch ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      FTRACE(0, j, 5);
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();     // order our tcgen05.ld/st before the MMAs that read / overwrite TMEM
       mbar_arrive(&p_ready[slot * 2 + buf]);
       FTRACE(0, j, 6);
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");  // red[] may be rewritten next step
-      FTRACE(0, j, 7);
+    };
+    if (n_mine > 0) load_s(0, sa);
+    for (int j = 0; j < n_mine; j += 2) {
+      step(j, sa, sb);
+      if (j + 1 < n_mine) step(j + 1, sb, sa);
     }
-    // ---- epilogue: combine the two partial row sums, read O from TMEM, normalise, store O (bf16) and LSE (log2 domain)
+    // ---- epilogue: read O from TMEM, normalise, store O (bf16) and LSE (log2 domain)
     if (n_mine > 0) {
-      mbar_wait(&o_done[slot], (n_mine - 1) & 1);   // all PVs done: this slot's P buffers are free -> fp32 scratch
+      mbar_wait(&o_done[slot], (n_mine - 1) & 1);
       tc_fence_after();
-      float* lsum = reinterpret_cast<float*>(smem + S::OFF_P + slot * 2 * S::P_BYTES);   // [half][128]
-      lsum[half * ATT_BQ + r_in] = l_part;
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-      const float l_run = l_part + lsum[(half ^ 1) * ATT_BQ + r_in];
+      const float l_run = l0 + l1;
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
       const bool row_ok = q_row < p.seq_q;
       __nv_bfloat16* op = p.o + (int64_t(b) * p.seq_q + q_row) * p.o_row_stride + int64_t(head) * p.o_head_stride;
 #pragma unroll
-      for (int ch = 0; ch < D / 64; ++ch) {
-        const int cc = half * (D / 64) + ch;
+      for (int cc = 0; cc < D / 32; ++cc) {
         uint32_t t[32];
         tmem_ld32(t_slot + 2 * ATT_BKV + cc * 32, t);
         tmem_ld_wait();
@@ -350,7 +349,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           }
         }
       }
-      if (row_ok && half == 0)
+      if (row_ok)
         p.lse[(int64_t(b) * p.nheads + head) * p.seq_q + q_row] = l_run > 0.f ? m_ref + log2f(l_run) : INFINITY;
     }
   }
@@ -411,6 +410,7 @@ extern "C" int fsb_sdpa_fwd(const void* q, const void* k, const void* v, void* o
   FSB_REQUIRE(head_dim == 64 || head_dim == 128, "sdpa_fwd: head_dim %d unsupported (64 or 128)", head_dim);
   FSB_REQUIRE(batch > 0 && seq_q > 0 && seq_kv > 0 && nheads > 0 && batch < 65536 && nheads < 65536, "sdpa_fwd: bad dims");
   FSB_REQUIRE(!causal || seq_q == seq_kv, "sdpa_fwd: causal needs seq_q == seq_kv");
+  FSB_REQUIRE(scale > 0.f, "sdpa_fwd: softmax scale must be positive");
   FSB_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), "sdpa_fwd: 16-byte alignment required");
   FSB_REQUIRE((q_row_stride | k_row_stride | v_row_stride | o_row_stride | q_head_stride | k_head_stride |
                v_head_stride | o_head_stride) % 8 == 0,

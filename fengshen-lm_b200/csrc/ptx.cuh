@@ -153,6 +153,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// same, into registers r[O .. O+31] of a larger array (keeps the array in registers: no pointer casts)
+template <int O, int N>
+__device__ __forceinline__ void tmem_ld32_at(uint32_t taddr, uint32_t (&r)[N]) {
+  static_assert(O + 32 <= N, "register window out of range");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[O + 0]), "=r"(r[O + 1]), "=r"(r[O + 2]), "=r"(r[O + 3]), "=r"(r[O + 4]), "=r"(r[O + 5]), "=r"(r[O + 6]), "=r"(r[O + 7]), "=r"(r[O + 8]), "=r"(r[O + 9]), "=r"(r[O + 10]), "=r"(r[O + 11]), "=r"(r[O + 12]), "=r"(r[O + 13]), "=r"(r[O + 14]), "=r"(r[O + 15]), "=r"(r[O + 16]), "=r"(r[O + 17]), "=r"(r[O + 18]), "=r"(r[O + 19]), "=r"(r[O + 20]), "=r"(r[O + 21]), "=r"(r[O + 22]), "=r"(r[O + 23]), "=r"(r[O + 24]), "=r"(r[O + 25]), "=r"(r[O + 26]), "=r"(r[O + 27]), "=r"(r[O + 28]), "=r"(r[O + 29]), "=r"(r[O + 30]), "=r"(r[O + 31])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // registers -> TMEM: this warp's 32 lanes x 32 consecutive fp32 columns (used to rescale an accumulator in place)
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -167,6 +179,9 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// register re-allocation between warpgroups (all 4 warps of a warpgroup must execute the same instruction)
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
