@@ -32,14 +32,17 @@ fn.argtypes = [ctypes.c_void_p]
 fn.restype = ctypes.c_int
 assert fn(buf) == 0
 t = np.array(buf, dtype=np.int64).reshape(2, 64, 8)
-n = min(S // 64, 64)
+n = min(S // 64, 63)
 base = t[0, 0, 0]
-print("softmax warp8: step | wait_s  ld+max  bar1  rescale  exp  stP+arrive  bar2 | step total")
+c = t[0, 63]
+print("CTA(0,0,0) warp 4: entry->setup %d | setup->first step %d | steps %d | o_done wait %d | epilogue %d | exit sync %d | total %d" % (
+    c[1]-c[0], base-c[1], c[2]-base, c[3]-c[2], c[4]-c[3], c[5]-c[4], c[5]-c[0]))
+print("softmax warp 4: step | decide(+o_done)  prefetch(s_full)  exp_lo  ld_wait+mask  exp_hi+max  fence+arrive | step total")
 for j in range(n):
     r = t[0, j]
-    nxt = t[0, j + 1, 0] if j + 1 < n else r[7]
-    print(f"{j:3d} | " + " ".join(f"{r[i+1]-r[i]:6d}" for i in range(7)) + f" | {nxt - r[0]:6d}   t0={r[0]-base}")
-print("mma warp (slot 1): step | wait_p  wait_kv  issue | total")
+    nxt = t[0, j + 1, 0] if j + 1 < n else r[6]
+    print(f"{j:3d} | " + " ".join(f"{r[i+1]-r[i]:6d}" for i in range(6)) + f" | {nxt - r[0]:6d}   t0={r[0]-base}")
+print("issue times relative to the softmax warp's step-0 start (slot 1 softmax step start | S1 PV1 | S0 PV0 | K load  V load):")
 for j in range(n):
-    r = t[1, j]
-    print(f"{j:3d} | {r[1]-r[0]:6d} {r[2]-r[1]:6d} {r[3]-r[2]:6d} | {r[3]-r[0]:6d}   t0={r[0]-base}")
+    r = t[1, j] - base
+    print(f"{j:3d} | step start {t[0, j, 0]-base:7d} | S1 {r[0]:7d} PV1 {r[1]:7d} | S0 {r[2]:7d} PV0 {r[3]:7d} | K {r[4]:7d} V {r[5]:7d}")
