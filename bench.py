@@ -281,6 +281,9 @@ def main():
     ap.add_argument("--per-gpu-batch", type=int, default=0, help="override sequences per GPU per step (profiling only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", action="store_true",
+                    help="after the timed runs, profile 2 more steps with CUDA events around every fsb_* call and print the "
+                         "per-entry-point time table to stderr (diagnostic; not part of the JSON line)")
     args = ap.parse_args()
     w = workload(args.workload)
     if args.micro_batch:
@@ -360,6 +363,28 @@ def main():
         ms2 = timed(lambda i: stepper.step(host[i % pool]), args.steps, world)
         e2e = {"value": args.gpus * tokens_per_step_gpu / (ms2 / args.steps / 1000.0), "unit": "tokens/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+
+    if args.breakdown and rank == 0:
+        bp = ops.KernelProfiler()
+        L.call_profiler = bp
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(2):
+            stepper.step_device(dev[i % pool])
+        ev1.record()
+        torch.cuda.synchronize()
+        L.call_profiler = None
+        tot = ev0.elapsed_time(ev1)
+        rows = sorted(bp.summary().items(), key=lambda kv: -kv[1]["ms"])
+        acc = sum(v["ms"] for _, v in rows)
+        print(f"[breakdown] 2 steps: {tot:.2f} ms wall on the stream; {acc:.2f} ms inside fsb_* calls "
+              f"({100 * acc / tot:.1f}%); the rest is torch-native kernels, NCCL and launch gaps", file=sys.stderr)
+        for name, v in rows:
+            print(f"[breakdown] {v['ms']:9.3f} ms {100 * v['ms'] / tot:6.2f}%  n={v['launches']:5d}  {name}", file=sys.stderr)
+    elif args.breakdown:
+        for i in range(2):
+            stepper.step_device(dev[i % pool])
 
     final_loss = float(losses[-1].item())
     if rank != 0:

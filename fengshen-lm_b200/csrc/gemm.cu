@@ -40,18 +40,20 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;       // 2 x [128 rows x 64 cols] bf16 staging tiles (TMA store)
-  static constexpr int STORE_BYTES = GEMM_BM * 64 * 2;
-  static constexpr int BAR_OFFSET = STORE_OFFSET + 2 * STORE_BYTES;
+  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;       // per epilogue warp: 2 x [32 rows x 64 cols] bf16 staging tiles
+  static constexpr int STORE_WARP_BYTES = 32 * 64 * 2;
+  static constexpr int BAR_OFFSET = STORE_OFFSET + 4 * 2 * STORE_WARP_BYTES;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024 /*align slack*/;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into on sm_100");
 };
 
+// 0.5 x (1 + tanh(u)) == x * sigmoid(2u) == x / (1 + 2^(-2 u log2 e)): two MUFU ops instead of tanhf's ~25 instructions
+// (relative error ~1e-6, far below the bf16 rounding of the stored activation)
 __device__ __forceinline__ float gelu_tanh_f(float x) {
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float u = k0 * x * (1.f + k1 * x * x);
-  return 0.5f * x * (1.f + tanhf(u));
+  const float k1 = 0.044715f, c = -2.f * 0.7978845608028654f * 1.4426950408889634f;
+  const float t = ex2_approx(c * x * fmaf(k1, x * x, 1.f));
+  return __fdividef(x, 1.f + t);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
 
@@ -71,7 +73,7 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
 template <int kLayout, int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmD, const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
   constexpr bool A_MN = (kLayout == FSB_GEMM_TN);
   constexpr bool B_MN = (kLayout != FSB_GEMM_NT);
   using S = GemmSmem<BN>;
@@ -179,10 +181,92 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32)
-    const int r_in = quad * 32 + lane;
-    const bool store_leader = (warp == 2 && lane == 0);
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (p.tma_store) {
+      // ---- bf16 D without accumulate (forward / dgrad GEMMs): every warp owns its 32 rows end to end.
+      // TMEM -> registers 64 columns at a time (the next group's tcgen05.ld is in flight while this one is converted),
+      // bias / activation in registers, bf16 rows into the warp's own 128B-swizzled [32 x 64] staging tile, one bulk tensor
+      // store per tile and warp: no CTA-wide barrier anywhere, and the accumulator is handed back to the MMA warp as soon
+      // as its last column has been read.
+      uint8_t* stg_w = smem + S::STORE_OFFSET + quad * (2 * S::STORE_WARP_BYTES);
+      uint32_t item = 0;                           // bulk stores issued by this warp (staging buffer = item & 1)
+      auto stage_store = [&](const uint32_t (&w)[32], const CUtensorMap* tm, int c0, int r0, int bz) {
+        uint8_t* stg = stg_w + (item & 1) * S::STORE_WARP_BYTES;
+        if (lane == 0) tma_store_wait_read<1>();   // the store issued two items ago has finished reading this buffer
+        __syncwarp();
+        const uint32_t row_addr = smem_u32(stg) + lane * 128;
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          st_shared_v4(row_addr + ((q ^ (lane & 7)) << 4), w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(tm, stg, c0, r0, bz);
+          tma_store_commit();
+        }
+        ++item;
+      };
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        int b, m_idx, n_idx;
+        tile_coords(t, p.tiles_m, p.tiles_n, b, m_idx, n_idx);
+        const int r0 = m_idx * GEMM_BM + quad * 32;
+        const int n0 = n_idx * BN;
+        constexpr int NG = BN / 64;
+        const int ng = min(NG, (p.N - n0 + 63) / 64);     // column groups of this tile that exist
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_acc = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+        uint32_t r[2][64];
+        tmem_ld32_at<0>(t_acc, r[0]);
+        tmem_ld32_at<32>(t_acc + 32, r[0]);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          if (g < ng) {                                    // warp-uniform
+            tmem_ld_wait();
+            if (g + 1 < ng) {
+              tmem_ld32_at<0>(t_acc + (g + 1) * 64, r[(g + 1) & 1]);
+              tmem_ld32_at<32>(t_acc + (g + 1) * 64 + 32, r[(g + 1) & 1]);
+            } else {                                       // last read of this accumulator: give it back to the MMA warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            }
+            uint32_t (&v)[64] = r[g & 1];
+            const int col0 = n0 + g * 64;
+            if (p.bias != nullptr) {
+              const bool full_cols = col0 + 64 <= p.N;
+#pragma unroll
+              for (int j = 0; j < 64; ++j) {
+                if (full_cols || col0 + j < p.N) {
+                  const float bv = p.bias_f32 ? __ldg(reinterpret_cast<const float*>(p.bias) + col0 + j)
+                                              : __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0 + j));
+                  v[j] = __float_as_uint(__uint_as_float(v[j]) + bv);
+                }
+              }
+            }
+            uint32_t w[32];
+            if (p.aux != nullptr) {                        // pre-activation copy (bf16) through its own tensor map
+#pragma unroll
+              for (int j = 0; j < 32; ++j) w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              stage_store(w, &tmAux, col0, r0, b);
+            }
+            if (p.epilogue == FSB_EPI_GELU_TANH) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(gelu_tanh_f(__uint_as_float(v[j])));
+            } else if (p.epilogue == FSB_EPI_GELU_ERF) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(gelu_erf_f(__uint_as_float(v[j])));
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+            stage_store(w, &tmD, col0, r0, b);
+          }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (lane == 0) tma_store_wait_read<0>();     // smem must outlive the last bulk stores' reads
+    } else
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int b, m_idx, n_idx;
       tile_coords(t, p.tiles_m, p.tiles_n, b, m_idx, n_idx);
@@ -234,30 +318,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_erf_f(v[j]);
         }
-        if (p.tma_store) {
-          // smem-staged, 128B-swizzled [128 x 64] tile per 64-column group, written back by one bulk tensor store
-          const int g = c >> 1, hb = c & 1;
-          uint8_t* stg = smem + S::STORE_OFFSET + (g & 1) * S::STORE_BYTES;
-          if (hb == 0) {  // buffer (g & 1) was last used two groups ago: its store must have finished READING smem
-            if (store_leader) tma_store_wait_read<1>();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 w;
-            w.x = pack_bf16x2(v[q * 8], v[q * 8 + 1]); w.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-            w.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]); w.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-            *reinterpret_cast<uint4*>(stg + r_in * 128 + (((hb * 4 + q) ^ (r_in & 7)) << 4)) = w;
-          }
-          if (hb == 1 || col0 + 32 >= p.N) {  // group complete (CTA-uniform)
-            fence_proxy_async();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (store_leader) {
-              tma_store_3d(&tmD, stg, n0 + g * 64, m_idx * GEMM_BM, b);
-              tma_store_commit();
-            }
-          }
-        } else if (row_ok) {
+        if (row_ok) {
           if (p.d_f32) {
             float* dp = reinterpret_cast<float*>(p.D) + int64_t(b) * p.stride_d + int64_t(row) * p.ldd + col0;
             if (full_cols) {
@@ -303,7 +364,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.tma_store && store_leader) tma_store_wait_read<0>();  // smem must outlive the last bulk store's reads
   }
 
   tc_fence_before();
@@ -315,8 +375,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int kLayout, int BN>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const GemmParams& p,
-                       cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAux,
+                       const GemmParams& p, cudaStream_t stream) {
   using S = GemmSmem<BN>;
   static bool configured = false;
   auto kern = gemm_bf16_kernel<kLayout, BN>;
@@ -330,7 +390,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   const int num_tiles = p.tiles_m * p.tiles_n * p.batch;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmD, p);
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmD, tmAux, p);
   FSB_CUDA_LAUNCH_CHECK();
   return FSB_OK;
 }
@@ -383,13 +443,18 @@ extern "C" int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K, const 
   }
   GemmParams p;
   p.tma_store = (d_dtype == FSB_BF16 && !accumulate) ? 1 : 0;
-  CUtensorMap tmD = tmA;  // placeholder when the bulk-store path is off
+  CUtensorMap tmD = tmA, tmAux = tmA;  // placeholders when the bulk-store path is off / there is no aux output
   if (p.tma_store) {
     uint64_t dims[3] = {uint64_t(N), uint64_t(M), uint64_t(batch)};
     uint64_t strides[2] = {uint64_t(ldd) * 2, uint64_t(batch > 1 ? stride_d : M * ldd) * 2};
-    uint32_t box[3] = {64, uint32_t(GEMM_BM), 1};
+    uint32_t box[3] = {64, 32, 1};   // one epilogue warp's rows x one 128-byte column group
     int rc = make_tmap_bf16(&tmD, D, 3, dims, strides, box);
     if (rc) return rc;
+    if (aux != nullptr) {
+      uint64_t astrides[2] = {uint64_t(ldaux) * 2, uint64_t(batch > 1 ? stride_aux : M * ldaux) * 2};
+      rc = make_tmap_bf16(&tmAux, aux, 3, dims, astrides, box);
+      if (rc) return rc;
+    }
   }
   p.D = D; p.aux = aux; p.bias = bias;
   p.ldd = ldd; p.ldaux = ldaux; p.stride_d = stride_d; p.stride_aux = stride_aux;
@@ -401,7 +466,7 @@ extern "C" int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K, const 
 
 #define FSB_GEMM_DISPATCH(L)                                                    \
   case L:                                                                        \
-    return BN == 256 ? launch_gemm<L, 256>(tmA, tmB, tmD, p, stream) : launch_gemm<L, 128>(tmA, tmB, tmD, p, stream);
+    return BN == 256 ? launch_gemm<L, 256>(tmA, tmB, tmD, tmAux, p, stream) : launch_gemm<L, 128>(tmA, tmB, tmD, tmAux, p, stream);
   switch (layout) {
     FSB_GEMM_DISPATCH(FSB_GEMM_NT)
     FSB_GEMM_DISPATCH(FSB_GEMM_NN)

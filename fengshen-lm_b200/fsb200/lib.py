@@ -112,11 +112,21 @@ _KERNELS_PER_CALL = {"fsb_rmsnorm_bwd": 2, "fsb_layernorm_bwd": 2, "fsb_softmax_
                      "fsb_sumsq": 2, "fsb_colsum": 2}
 
 
+call_profiler = None  # optional: object with .add(name, ev0, ev1, work); set by bench.py --breakdown (CUDA events per call)
+
+
 def call(name, *args):
     """Invoke a status-returning entry point and raise on error."""
     global launch_count, kernel_launches
     launch_count += 1
     kernel_launches += _KERNELS_PER_CALL.get(name, 1)
-    rc = getattr(load(), name)(*args)
+    if call_profiler is not None:
+        import torch
+        ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
+        rc = getattr(load(), name)(*args)
+        ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
+        call_profiler.add(name, ev0, ev1, 0.0)
+    else:
+        rc = getattr(load(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"fsb200: {name} failed (status {rc}): {last_error()}")

@@ -35,6 +35,12 @@ def main():
         ("gpt2 head fwd", L.GEMM_NT, 32768, 50264, 768),
         ("square 8192", L.GEMM_NT, 8192, 8192, 8192),
     ]
+    if len(sys.argv) > 1 and sys.argv[1] == "gpt2":   # every GEMM of a Wenzhong-GPT2-110M step (tokens = 32 x 1024)
+        T, h, V = 32768, 768, 50264
+        shapes = []
+        for nm, i, o in [("c_attn", h, 3 * h), ("c_proj", h, h), ("c_fc", h, 4 * h), ("mlp_proj", 4 * h, h)]:
+            shapes += [(nm + " fwd", L.GEMM_NN, T, o, i), (nm + " dgrad", L.GEMM_NT, T, i, o), (nm + " wgrad", L.GEMM_TN, i, o, T)]
+        shapes += [("head fwd", L.GEMM_NT, T, V, h), ("head dgrad", L.GEMM_NN, T, h, V), ("head wgrad", L.GEMM_TN, V, h, T)]
     for name, layout, M, N, K in shapes:
         if layout == L.GEMM_NT:
             a = torch.randn(M, K, device=dev, dtype=torch.bfloat16); b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
