@@ -42,7 +42,8 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;       // per epilogue warp: 2 x [32 rows x 64 cols] bf16 staging tiles
   static constexpr int STORE_WARP_BYTES = 32 * 64 * 2;
-  static constexpr int BAR_OFFSET = STORE_OFFSET + 4 * 2 * STORE_WARP_BYTES;
+  static constexpr int BIAS_OFFSET = STORE_OFFSET + 4 * 2 * STORE_WARP_BYTES;   // 2 x [BN] bf16: this tile's bias slice
+  static constexpr int BAR_OFFSET = BIAS_OFFSET + 2 * BN * 2;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024 /*align slack*/;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into on sm_100");
@@ -220,6 +221,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t r[2][64];
         tmem_ld32_at<0>(t_acc, r[0]);
         tmem_ld32_at<32>(t_acc + 32, r[0]);
+        // bias slice of this tile -> shared memory as bf16 (the four epilogue warps write identical values, so only a
+        // __syncwarp is needed; two buffers because a warp may run one tile ahead of its slowest sibling)
+        __nv_bfloat16* sbias = reinterpret_cast<__nv_bfloat16*>(smem + S::BIAS_OFFSET) + acc * BN;
+        float bias_reg[BN / 32];                   // fp32 bias: lane l keeps columns c*32 + l, broadcast by shuffle (exact)
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) {
+            const int col = n0 + c * 32 + lane;
+            bias_reg[c] = 0.f;
+            if (p.bias_f32) {
+              if (col < p.N) bias_reg[c] = __ldg(reinterpret_cast<const float*>(p.bias) + col);
+            } else {
+              sbias[c * 32 + lane] = col < p.N ? __ldg(reinterpret_cast<const __nv_bfloat16*>(p.bias) + col) : __float2bfloat16(0.f);
+            }
+          }
+          __syncwarp();
+        }
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
           if (g < ng) {                                    // warp-uniform
@@ -234,14 +252,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             uint32_t (&v)[64] = r[g & 1];
             const int col0 = n0 + g * 64;
-            if (p.bias != nullptr) {
-              const bool full_cols = col0 + 64 <= p.N;
+            if (p.bias != nullptr && p.bias_f32) {
 #pragma unroll
-              for (int j = 0; j < 64; ++j) {
-                if (full_cols || col0 + j < p.N) {
-                  const float bv = p.bias_f32 ? __ldg(reinterpret_cast<const float*>(p.bias) + col0 + j)
-                                              : __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(p.bias) + col0 + j));
-                  v[j] = __float_as_uint(__uint_as_float(v[j]) + bv);
+              for (int j = 0; j < 64; ++j)
+                v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bias_reg[g * 2 + (j >> 5)], j & 31));
+            } else if (p.bias != nullptr) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {                // broadcast 16-byte reads: 8 bias values each
+                const uint4 bq = *reinterpret_cast<const uint4*>(sbias + g * 64 + q * 8);
+                const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  v[q * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[q * 8 + 2 * e]) + bf16lo(bw[e]));
+                  v[q * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[q * 8 + 2 * e + 1]) + bf16hi(bw[e]));
                 }
               }
             }

@@ -115,8 +115,8 @@ _KERNELS_PER_CALL = {"fsb_rmsnorm_bwd": 2, "fsb_layernorm_bwd": 2, "fsb_softmax_
 call_profiler = None  # optional: object with .add(name, ev0, ev1, work); set by bench.py --breakdown (CUDA events per call)
 
 
-def call(name, *args):
-    """Invoke a status-returning entry point and raise on error."""
+def call(name, *args, tag=None):
+    """Invoke a status-returning entry point and raise on error. `tag` refines the profiler key (e.g. the GEMM shape)."""
     global launch_count, kernel_launches
     launch_count += 1
     kernel_launches += _KERNELS_PER_CALL.get(name, 1)
@@ -125,7 +125,7 @@ def call(name, *args):
         ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
         rc = getattr(load(), name)(*args)
         ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
-        call_profiler.add(name, ev0, ev1, 0.0)
+        call_profiler.add(name if tag is None else f"{name} {tag}", ev0, ev1, 0.0)
     else:
         rc = getattr(load(), name)(*args)
     if rc != 0:

@@ -80,7 +80,10 @@ def gemm(layout, a, b, out=None, out_dtype=_bf16, bias=None, epilogue=L.EPI_NONE
         ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
     L.call("fsb_gemm_bf16", layout, M, N, K, _p(a), lda, _p(b), ldb, _p(out), ldd,
            L.F32 if out.dtype == torch.float32 else L.BF16, _p(bias), bias_dt, epilogue, int(bool(accumulate)),
-           _p(aux), ldaux, 1, 0, 0, 0, 0, _stream())
+           _p(aux), ldaux, 1, 0, 0, 0, 0, _stream(),
+           tag=(f"{('NT', 'NN', 'TN')[layout]} {M}x{N}x{K} epi{epilogue} acc{int(bool(accumulate))} "
+                f"{'f32' if out.dtype == torch.float32 else 'bf16'}{' bias' if bias is not None else ''}"
+                f"{' aux' if aux is not None else ''}") if L.call_profiler is not None else None)
     if prof is not None:
         ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
         prof.add("gemm_bf16_kernel", ev0, ev1, 2.0 * M * N * K)
