@@ -418,6 +418,53 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return FSB_OK;
 }
 
+// D (bf16 / fp32, optionally accumulated into) = sum over the K-splits of the fp32 partial products, in a fixed order
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t M, int64_t N, void* D, int64_t ldd,
+                                     int d_f32, int accumulate) {
+  const int64_t n4 = N / 4;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < M * n4; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t m = i / n4, n = (i - m * n4) * 4;
+    float4 acc = *reinterpret_cast<const float4*>(ws + m * N + n);
+    for (int s = 1; s < splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + (int64_t(s) * M + m) * N + n);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (d_f32) {
+      float4* dp = reinterpret_cast<float4*>(reinterpret_cast<float*>(D) + m * ldd + n);
+      if (accumulate) { const float4 o = *dp; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+      *dp = acc;
+    } else {
+      uint2* dp = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(D) + m * ldd + n);
+      if (accumulate) {
+        const uint2 o = *dp;
+        acc.x += bf16lo(o.x); acc.y += bf16hi(o.x); acc.z += bf16lo(o.y); acc.w += bf16hi(o.y);
+      }
+      *dp = make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+    }
+  }
+}
+
+// Scratch for split-K partial products: one lazily grown buffer per device. fsb_gemm_bf16 calls that split K must not run
+// concurrently on several streams of the same device (the training step issues all GEMMs on one stream).
+static void* g_splitk_ws[16] = {};
+static size_t g_splitk_bytes[16] = {};
+static float* splitk_workspace(size_t bytes) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (g_splitk_bytes[dev] < bytes) {
+    if (g_splitk_ws[dev]) { cudaDeviceSynchronize(); cudaFree(g_splitk_ws[dev]); }
+    g_splitk_ws[dev] = nullptr; g_splitk_bytes[dev] = 0;
+    if (cudaMalloc(&g_splitk_ws[dev], bytes) != cudaSuccess) return nullptr;
+    g_splitk_bytes[dev] = bytes;
+  }
+  return static_cast<float*>(g_splitk_ws[dev]);
+}
+
+static int gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                     int64_t ldb, void* D, int64_t ldd, int d_dtype, const void* bias, int bias_dtype,
+                     int epilogue, int accumulate, void* aux, int64_t ldaux, int64_t batch, int64_t stride_a,
+                     int64_t stride_b, int64_t stride_d, int64_t stride_aux, cudaStream_t stream);
+
 }  // namespace fsb
 
 using namespace fsb;
@@ -427,6 +474,37 @@ extern "C" int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K, const 
                              int epilogue, int accumulate, void* aux, int64_t ldaux, int64_t batch, int64_t stride_a,
                              int64_t stride_b, int64_t stride_d, int64_t stride_aux, fsb_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // Split-K for weight-gradient GEMMs whose output has too few tiles to occupy the SMs (e.g. 768 x 768 x 32768: 36 tiles):
+  // run `splits` K-chunks as a batched GEMM into an fp32 scratch, then sum the chunks in a fixed order (deterministic).
+  if (layout == FSB_GEMM_TN && batch == 1 && bias == nullptr && aux == nullptr && epilogue == FSB_EPI_NONE && M > 0 &&
+      N > 0 && N % 4 == 0 && (M * N) % 8 == 0 && K >= 4096 && (d_dtype == FSB_BF16 || d_dtype == FSB_F32)) {
+    const int64_t tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + 127) / 128);
+    int splits = int(num_sms() / tiles);
+    if (splits > 16) splits = 16;
+    while (splits > 1 && (K % (int64_t(splits) * GEMM_BK) != 0 || K / splits < 1024)) --splits;
+    if (splits >= 2 && tiles * 2 <= num_sms()) {
+      float* ws = splitk_workspace(size_t(splits) * M * N * sizeof(float));
+      if (ws == nullptr) { set_error("gemm: cannot allocate the split-K scratch (%zu bytes)", size_t(splits) * M * N * 4); return FSB_ERR_CUDA; }
+      const int64_t kc = K / splits;
+      int rc = gemm_impl(layout, M, N, kc, A, lda, B, ldb, ws, N, FSB_F32, nullptr, FSB_BF16, FSB_EPI_NONE, 0, nullptr, 0,
+                         splits, kc * lda, kc * ldb, M * N, 0, stream);
+      if (rc) return rc;
+      FSB_REQUIRE(ldd % 4 == 0, "gemm: ldd=%ld not vector-aligned", (long)ldd);
+      const int64_t work = M * (N / 4);
+      const int blocks = int(work / 256 + 1 < 2 * num_sms() ? work / 256 + 1 : 2 * num_sms());
+      splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(ws, splits, M, N, D, ldd, d_dtype == FSB_F32, accumulate);
+      FSB_CUDA_LAUNCH_CHECK();
+      return FSB_OK;
+    }
+  }
+  return gemm_impl(layout, M, N, K, A, lda, B, ldb, D, ldd, d_dtype, bias, bias_dtype, epilogue, accumulate, aux, ldaux, batch,
+                   stride_a, stride_b, stride_d, stride_aux, stream);
+}
+
+static int fsb::gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                          int64_t ldb, void* D, int64_t ldd, int d_dtype, const void* bias, int bias_dtype,
+                          int epilogue, int accumulate, void* aux, int64_t ldaux, int64_t batch, int64_t stride_a,
+                          int64_t stride_b, int64_t stride_d, int64_t stride_aux, cudaStream_t stream) {
   FSB_REQUIRE(layout >= 0 && layout <= 2, "gemm: bad layout %d", layout);
   FSB_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "gemm: non-positive dims M=%ld N=%ld K=%ld batch=%ld", (long)M,
               (long)N, (long)K, (long)batch);

@@ -71,6 +71,25 @@ def test_gemm_bias_gelu_aux_accumulate():
     assert outbig[:, :N].abs().max().item() == 0.0
 
 
+def test_gemm_splitk_wgrad():
+    """Weight-gradient GEMMs with few output tiles take the split-K path (batched fp32 partials + ordered reduction)."""
+    M, N, K = 384, 256, 8192          # 6 tiles of 128x128 -> K split over several CTAs per tile
+    a, b = _rand(K, M, seed=7, scale=0.5), _rand(K, N, seed=8, scale=0.5)
+    ref = a.float().t() @ b.float()
+    out = ops.gemm(L.GEMM_TN, a, b)
+    _close(out, ref, atol=2e-2 * math.sqrt(K / 64), rtol=1e-2, what="split-K bf16")
+    out32 = ops.gemm(L.GEMM_TN, a, b, out_dtype=torch.float32)
+    _close(out32, ref, atol=1e-3 * math.sqrt(K / 64), rtol=1e-4, what="split-K fp32")
+    acc = torch.full((M, N), 2.0, dtype=torch.float32, device=DEV)
+    ops.gemm(L.GEMM_TN, a, b, out=acc, accumulate=True)
+    _close(acc, ref + 2.0, atol=1e-3 * math.sqrt(K / 64), rtol=1e-4, what="split-K fp32 accumulate")
+    accb = torch.ones(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(L.GEMM_TN, a, b, out=accb, accumulate=True)
+    _close(accb, ref + 1.0, atol=2e-2 * math.sqrt(K / 64), rtol=1e-2, what="split-K bf16 accumulate")
+    again = ops.gemm(L.GEMM_TN, a, b)
+    assert torch.equal(out, again), "split-K must be deterministic"
+
+
 def test_gemm_rejects_bad_arguments():
     a = _rand(64, 60)  # lda = 60 not a multiple of 8
     b = _rand(64, 60)
