@@ -7,9 +7,11 @@
 //   TN  D = A[K,M]^T B[K,N]   A and B MN-major                (wgrad)
 // MN-major tiles are fetched as 64(mn) x 64(k) TMA boxes; the UMMA descriptor's leading-byte-offset walks the boxes.
 //
-// Roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 = epilogue
-// (TMEM lane quadrant = warp_id % 4). Two TMEM accumulator stages let the epilogue of tile i overlap the
-// main loop of tile i+1. Grid = min(#tiles, #SMs); static round-robin tile order, grouped 8 m-tiles deep for L2.
+// Roles (384 threads = 3 warpgroups): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-3 idle (they only
+// donate registers: setmaxnreg moves the budget of warpgroup 0 to the epilogue), warps 4..11 = epilogue: TMEM lane
+// quadrant = warp_id % 4, and the two warps of a quadrant split the tile's 64-column groups between them (bias /
+// activation / bf16 conversion are instruction-bound with one warp per scheduler). Two TMEM accumulator stages let the
+// epilogue of tile i overlap the main loop of tile i+1. Grid = min(#tiles, #SMs); static round-robin tile order, grouped 8 m-tiles deep for L2.
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -17,7 +19,8 @@ namespace fsb {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARP0 = 4;   // first epilogue warp
 constexpr int GEMM_GROUP_M = 8;
 
 struct GemmParams {
@@ -34,15 +37,19 @@ struct GemmParams {
   int tiles_m, tiles_n;
 };
 
-template <int BN>
+// kAux: the GEMM also writes the pre-activation (GELU MLPs): two bulk stores per column group. Their smem->global reads
+// queue behind the mainloop's TMA loads, so that variant trades one operand stage (K is the hidden size there, short
+// mainloops) for a four-deep staging ring per epilogue warp.
+template <int BN, bool kAux>
 struct GemmSmem {
-  static constexpr int STAGES = BN == 256 ? 4 : 6;
+  static constexpr int STAGES = BN == 256 ? (kAux ? 3 : 4) : (kAux ? 5 : 6);
+  static constexpr int NBUF = kAux ? 4 : 2;                        // staging tiles per epilogue warp
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
   static constexpr int B_BYTES = BN * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;       // per epilogue warp: 2 x [32 rows x 64 cols] bf16 staging tiles
+  static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;       // per epilogue warp: NBUF x [32 rows x 64 cols] bf16 staging tiles
   static constexpr int STORE_WARP_BYTES = 32 * 64 * 2;
-  static constexpr int BIAS_OFFSET = STORE_OFFSET + 4 * 2 * STORE_WARP_BYTES;   // 2 x [BN] bf16: this tile's bias slice
+  static constexpr int BIAS_OFFSET = STORE_OFFSET + 4 * NBUF * STORE_WARP_BYTES;   // 2 x [BN] bf16: this tile's bias slice
   static constexpr int BAR_OFFSET = BIAS_OFFSET + 2 * BN * 2;
   // full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem_ptr
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024 /*align slack*/;
@@ -56,7 +63,20 @@ __device__ __forceinline__ float gelu_tanh_f(float x) {
   const float t = ex2_approx(c * x * fmaf(k1, x * x, 1.f));
   return __fdividef(x, 1.f + t);
 }
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865476f)); }
+// 0.5 x (1 + erf(x / sqrt 2)) with erfc from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the
+// stored activation): erfc(z) ~= t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2), t = 1 / (1 + 0.3275911 z), z = |x| / sqrt 2.
+// Written on erfc so that the negative branch (1 + erf = erfc(|z|)) has no cancellation. ~12 instructions instead of erff's ~40.
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  const float z = fabsf(x) * 0.7071067811865476f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float pl = fmaf(t, 1.061405429f, -1.453152027f);
+  pl = fmaf(t, pl, 1.421413741f);
+  pl = fmaf(t, pl, -0.284496736f);
+  pl = fmaf(t, pl, 0.254829592f);
+  const float erfc_z = pl * t * ex2_approx(-1.4426950408889634f * z * z);
+  const float hx = 0.5f * x;
+  return x >= 0.f ? fmaf(-hx, erfc_z, x) : hx * erfc_z;
+}
 
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& b, int& m_idx, int& n_idx) {
   const int per = tiles_m * tiles_n;
@@ -71,13 +91,13 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   n_idx = in_g / gsize;
 }
 
-template <int kLayout, int BN>
+template <int kLayout, int BN, bool kAux>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
   constexpr bool A_MN = (kLayout == FSB_GEMM_TN);
   constexpr bool B_MN = (kLayout != FSB_GEMM_NT);
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, kAux>;
   constexpr int STAGES = S::STAGES;
   constexpr uint32_t IDESC = make_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
   constexpr int TMEM_COLS = 2 * BN;  // 512 or 256
@@ -104,7 +124,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], p.tma_store ? 8 : 4);  // one arrive per participating epilogue warp
     }
     fence_barrier_init();
   }
@@ -116,6 +136,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
+    reg_dec<40>();
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -149,6 +170,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
+    reg_dec<40>();
     const uint64_t dsc_a = A_MN ? make_smem_desc_sw128(smem_u32(smem), GEMM_BK * 128, 1024)
                                 : make_smem_desc_sw128(smem_u32(smem), 0, 1024);
     const uint64_t dsc_b = B_MN ? make_smem_desc_sw128(smem_u32(smem) + S::A_BYTES, GEMM_BK * 128, 1024)
@@ -179,9 +201,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+  } else if (warp < GEMM_EPI_WARP0) {
+    reg_dec<40>();   // idle register donors
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32)
+    // ===================== epilogue (warps 4..11) =====================
+    reg_inc<232>();  // 256 * 232 + 128 * 40 = 384 * 168
+    const int quad = warp & 3;                        // TMEM lanes [32*quad, 32*quad+32)
+    const int half = (warp - GEMM_EPI_WARP0) >> 2;    // which of the quadrant's two warps
     int acc = 0;
     uint32_t acc_phase = 0;
     if (p.tma_store) {
@@ -190,11 +216,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // bias / activation in registers, bf16 rows into the warp's own 128B-swizzled [32 x 64] staging tile, one bulk tensor
       // store per tile and warp: no CTA-wide barrier anywhere, and the accumulator is handed back to the MMA warp as soon
       // as its last column has been read.
-      uint8_t* stg_w = smem + S::STORE_OFFSET + quad * (2 * S::STORE_WARP_BYTES);
-      uint32_t item = 0;                           // bulk stores issued by this warp (staging buffer = item & 1)
+      constexpr int NBW = S::NBUF / 2;             // staging tiles per warp
+      uint8_t* stg_w = smem + S::STORE_OFFSET + (half * 4 + quad) * (NBW * S::STORE_WARP_BYTES);
+      uint32_t item = 0;                           // bulk stores issued by this warp (staging buffer = item % NBW)
       auto stage_store = [&](const uint32_t (&w)[32], const CUtensorMap* tm, int c0, int r0, int bz) {
-        uint8_t* stg = stg_w + (item & 1) * S::STORE_WARP_BYTES;
-        if (lane == 0) tma_store_wait_read<1>();   // the store issued two items ago has finished reading this buffer
+        uint8_t* stg = stg_w + (item % NBW) * S::STORE_WARP_BYTES;
+        if (lane == 0) tma_store_wait_read<NBW - 1>();   // the store issued NBW items ago has finished reading this buffer
         __syncwarp();
         const uint32_t row_addr = smem_u32(stg) + lane * 128;
 #pragma unroll
@@ -218,44 +245,56 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_acc = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
+        constexpr int NGW = NG / 2;                        // column groups per warp: g = 2 * i + half
+        if (half >= ng) {                                  // (ragged last tile) nothing for this warp: just release
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         uint32_t r[2][64];
-        tmem_ld32_at<0>(t_acc, r[0]);
-        tmem_ld32_at<32>(t_acc + 32, r[0]);
-        // bias slice of this tile -> shared memory as bf16 (the four epilogue warps write identical values, so only a
+        tmem_ld32_at<0>(t_acc + half * 64, r[0]);
+        tmem_ld32_at<32>(t_acc + half * 64 + 32, r[0]);
+        // bias slice of this tile -> shared memory as bf16 (all epilogue warps write identical values, so only a
         // __syncwarp is needed; two buffers because a warp may run one tile ahead of its slowest sibling)
         __nv_bfloat16* sbias = reinterpret_cast<__nv_bfloat16*>(smem + S::BIAS_OFFSET) + acc * BN;
-        float bias_reg[BN / 32];                   // fp32 bias: lane l keeps columns c*32 + l, broadcast by shuffle (exact)
+        float bias_reg[NGW * 2];                   // fp32 bias: lane l keeps this warp's columns, broadcast by shuffle (exact)
         if (p.bias != nullptr) {
+          if (p.bias_f32) {
 #pragma unroll
-          for (int c = 0; c < BN / 32; ++c) {
-            const int col = n0 + c * 32 + lane;
-            bias_reg[c] = 0.f;
-            if (p.bias_f32) {
-              if (col < p.N) bias_reg[c] = __ldg(reinterpret_cast<const float*>(p.bias) + col);
-            } else {
+            for (int c = 0; c < NGW * 2; ++c) {
+              const int col = n0 + (2 * (c >> 1) + half) * 64 + (c & 1) * 32 + lane;
+              bias_reg[c] = col < p.N ? __ldg(reinterpret_cast<const float*>(p.bias) + col) : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+              const int col = n0 + c * 32 + lane;
               sbias[c * 32 + lane] = col < p.N ? __ldg(reinterpret_cast<const __nv_bfloat16*>(p.bias) + col) : __float2bfloat16(0.f);
             }
           }
           __syncwarp();
         }
 #pragma unroll
-        for (int g = 0; g < NG; ++g) {
+        for (int i = 0; i < NGW; ++i) {
+          const int g = 2 * i + half;
           if (g < ng) {                                    // warp-uniform
             tmem_ld_wait();
-            if (g + 1 < ng) {
-              tmem_ld32_at<0>(t_acc + (g + 1) * 64, r[(g + 1) & 1]);
-              tmem_ld32_at<32>(t_acc + (g + 1) * 64 + 32, r[(g + 1) & 1]);
+            if (i + 1 < NGW && g + 2 < ng) {
+              tmem_ld32_at<0>(t_acc + (g + 2) * 64, r[(i + 1) & 1]);
+              tmem_ld32_at<32>(t_acc + (g + 2) * 64 + 32, r[(i + 1) & 1]);
             } else {                                       // last read of this accumulator: give it back to the MMA warp
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&tmem_empty[acc]);
             }
-            uint32_t (&v)[64] = r[g & 1];
+            uint32_t (&v)[64] = r[i & 1];
             const int col0 = n0 + g * 64;
             if (p.bias != nullptr && p.bias_f32) {
 #pragma unroll
               for (int j = 0; j < 64; ++j)
-                v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bias_reg[g * 2 + (j >> 5)], j & 31));
+                v[j] = __float_as_uint(__uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bias_reg[i * 2 + (j >> 5)], j & 31));
             } else if (p.bias != nullptr) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) {                // broadcast 16-byte reads: 8 bias values each
@@ -269,7 +308,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             uint32_t w[32];
-            if (p.aux != nullptr) {                        // pre-activation copy (bf16) through its own tensor map
+            if (kAux && p.aux != nullptr) {                // pre-activation copy (bf16) through its own tensor map
 #pragma unroll
               for (int j = 0; j < 32; ++j) w[j] = pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
               stage_store(w, &tmAux, col0, r0, b);
@@ -289,7 +328,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (lane == 0) tma_store_wait_read<0>();     // smem must outlive the last bulk stores' reads
-    } else
+    } else if (half == 0)
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int b, m_idx, n_idx;
       tile_coords(t, p.tiles_m, p.tiles_n, b, m_idx, n_idx);
@@ -397,12 +436,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-template <int kLayout, int BN>
+template <int kLayout, int BN, bool kAux>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAux,
                        const GemmParams& p, cudaStream_t stream) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, kAux>;
   static bool configured = false;
-  auto kern = gemm_bf16_kernel<kLayout, BN>;
+  auto kern = gemm_bf16_kernel<kLayout, BN, kAux>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) {
@@ -567,7 +606,11 @@ static int fsb::gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const voi
 
 #define FSB_GEMM_DISPATCH(L)                                                    \
   case L:                                                                        \
-    return BN == 256 ? launch_gemm<L, 256>(tmA, tmB, tmD, tmAux, p, stream) : launch_gemm<L, 128>(tmA, tmB, tmD, tmAux, p, stream);
+    if (p.tma_store && aux != nullptr)                                                                           \
+      return BN == 256 ? launch_gemm<L, 256, true>(tmA, tmB, tmD, tmAux, p, stream)                               \
+                       : launch_gemm<L, 128, true>(tmA, tmB, tmD, tmAux, p, stream);                              \
+    return BN == 256 ? launch_gemm<L, 256, false>(tmA, tmB, tmD, tmAux, p, stream)                                \
+                     : launch_gemm<L, 128, false>(tmA, tmB, tmD, tmAux, p, stream);
   switch (layout) {
     FSB_GEMM_DISPATCH(FSB_GEMM_NT)
     FSB_GEMM_DISPATCH(FSB_GEMM_NN)

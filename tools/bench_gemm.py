@@ -41,6 +41,18 @@ def main():
         for nm, i, o in [("c_attn", h, 3 * h), ("c_proj", h, h), ("c_fc", h, 4 * h), ("mlp_proj", 4 * h, h)]:
             shapes += [(nm + " fwd", L.GEMM_NN, T, o, i), (nm + " dgrad", L.GEMM_NT, T, i, o), (nm + " wgrad", L.GEMM_TN, i, o, T)]
         shapes += [("head fwd", L.GEMM_NT, T, V, h), ("head dgrad", L.GEMM_NN, T, h, V), ("head wgrad", L.GEMM_TN, V, h, T)]
+    if len(sys.argv) > 1 and sys.argv[1] == "epi":    # epilogue variants of the GPT2 c_fc forward GEMM
+        T, h = 32768, 768
+        a = torch.randn(T, h, device=dev, dtype=torch.bfloat16); w = torch.randn(h, 4 * h, device=dev, dtype=torch.bfloat16) * 0.05
+        bias = torch.randn(4 * h, device=dev, dtype=torch.bfloat16)
+        out = torch.empty(T, 4 * h, device=dev, dtype=torch.bfloat16); aux = torch.empty_like(out)
+        for nm, kw in [("plain", {}), ("bias", dict(bias=bias)), ("bias+aux", dict(bias=bias, aux=aux)),
+                       ("bias+gelu_tanh", dict(bias=bias, epilogue=L.EPI_GELU_TANH)),
+                       ("bias+gelu_tanh+aux", dict(bias=bias, epilogue=L.EPI_GELU_TANH, aux=aux)),
+                       ("bias+gelu_erf+aux", dict(bias=bias, epilogue=L.EPI_GELU_ERF, aux=aux))]:
+            t = timeit(lambda: ops.gemm(L.GEMM_NN, a, w, out=out, **kw))
+            print(f"c_fc fwd {nm:22s} {t:8.3f} ms {2.0 * T * h * 4 * h / t / 1e9:8.1f} TF", flush=True)
+        return
     for name, layout, M, N, K in shapes:
         if layout == L.GEMM_NT:
             a = torch.randn(M, K, device=dev, dtype=torch.bfloat16); b = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
