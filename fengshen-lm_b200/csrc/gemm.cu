@@ -21,7 +21,6 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARP0 = 4;   // first epilogue warp
-constexpr int GEMM_GROUP_M = 8;
 
 struct GemmParams {
   void* D;
@@ -35,6 +34,7 @@ struct GemmParams {
   int accumulate;  // D += result
   int tma_store;   // bf16 D without accumulate: stage through smem and write with cp.async.bulk.tensor (full lines)
   int tiles_m, tiles_n;
+  int group_m;     // m-tiles per rasterisation group (see fsb_gemm_bf16)
 };
 
 // kAux: the GEMM also writes the pre-activation (GELU MLPs): two bulk stores per column group. Their smem->global reads
@@ -78,14 +78,14 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return x >= 0.f ? fmaf(-hx, erfc_z, x) : hx * erfc_z;
 }
 
-__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& b, int& m_idx, int& n_idx) {
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& b, int& m_idx, int& n_idx) {
   const int per = tiles_m * tiles_n;
   b = t / per;
   int r = t - b * per;
-  const int group_span = GEMM_GROUP_M * tiles_n;
+  const int group_span = group_m * tiles_n;
   const int g = r / group_span;
-  const int first_m = g * GEMM_GROUP_M;
-  const int gsize = min(tiles_m - first_m, GEMM_GROUP_M);
+  const int first_m = g * group_m;
+  const int gsize = min(tiles_m - first_m, group_m);
   const int in_g = r - g * group_span;
   m_idx = first_m + in_g % gsize;
   n_idx = in_g / gsize;
@@ -142,7 +142,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int b, m_idx, n_idx;
-        tile_coords(t, p.tiles_m, p.tiles_n, b, m_idx, n_idx);
+        tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, b, m_idx, n_idx);
         const int m0 = m_idx * GEMM_BM, n0 = n_idx * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -237,7 +237,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       };
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         int b, m_idx, n_idx;
-        tile_coords(t, p.tiles_m, p.tiles_n, b, m_idx, n_idx);
+        tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, b, m_idx, n_idx);
         const int r0 = m_idx * GEMM_BM + quad * 32;
         const int n0 = n_idx * BN;
         constexpr int NG = BN / 64;
@@ -331,7 +331,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (half == 0)
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int b, m_idx, n_idx;
-      tile_coords(t, p.tiles_m, p.tiles_n, b, m_idx, n_idx);
+      tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, b, m_idx, n_idx);
       const int row = m_idx * GEMM_BM + quad * 32 + lane;
       const int n0 = n_idx * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -603,6 +603,18 @@ static int fsb::gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const voi
   p.epilogue = epilogue; p.accumulate = accumulate;
   p.tiles_m = int((M + GEMM_BM - 1) / GEMM_BM);
   p.tiles_n = int((N + BN - 1) / BN);
+  // Rasterisation: tiles are walked m-fastest inside groups of group_m m-tiles, so one wave of CTAs touches group_m A panels
+  // and #SMs/group_m B panels. HBM traffic per wave is minimal when both sides weigh the same (group_m ~ sqrt(#SMs * BN/BM):
+  // 16 for 256-wide tiles, 12 for 128-wide ones); measured with ncu, panels do not survive in the L2 from one wave to the next
+  // unless they are small (the two dies' L2 halves mirror shared lines), so the group only grows beyond that while its A panels
+  // (group_m x 128 x K bf16) stay under ~32 MB (ncu: 8192x15360x5120 reads 1379 MB at group_m 8, 584 MB at 24; 241 MB algorithmic).
+  {
+    const int64_t a_panel = int64_t(GEMM_BM) * K * 2;
+    const int64_t base = BN == 256 ? 16 : 12;
+    int64_t gm = (int64_t(32) << 20) / a_panel;
+    gm = gm < base ? base : (gm > 64 ? 64 : gm);
+    p.group_m = int(gm);
+  }
 
 #define FSB_GEMM_DISPATCH(L)                                                    \
   case L:                                                                        \
