@@ -19,9 +19,14 @@ namespace fsb {
 int make_attn_tmap(CUtensorMap* tm, const void* base, int64_t row_stride, int64_t width, int64_t seq, int64_t batch,
                    int box_rows);
 
-constexpr int AB_THREADS = 320;  // warps 0-7: math (2 threads per row, 32 columns each); warp 8: TMA; warp 9: MMA + TMEM owner
-constexpr int AB_MATH = 256;
-constexpr int AB_W_TMA = 8, AB_W_MMA = 9;
+// warps 0-15: math — 4 threads per row, 16 of the step's 64 columns each (warp w: TMEM lane quadrant w & 3, column part w >> 2).
+// The per-step chain (tcgen05.ld -> exp2 / multiply -> bf16 tile in smem -> arrive) is latency-bound, so four warps per
+// scheduler with a quarter of the work each beat two with half each. warp 16: TMA; warp 17: MMA + TMEM owner.
+constexpr int AB_PARTS = 4;
+constexpr int AB_PC = 64 / AB_PARTS;   // columns per thread and step
+constexpr int AB_MATH = 128 * AB_PARTS;
+constexpr int AB_THREADS = AB_MATH + 64;
+constexpr int AB_W_TMA = AB_MATH / 32, AB_W_MMA = AB_MATH / 32 + 1;
 
 constexpr int AB_BM = 128;       // rows owned by the CTA (queries for dQ, keys for dKV) == TMEM lanes
 constexpr int AB_BN = 64;        // streamed tile (keys for dQ, queries for dKV)
@@ -136,7 +141,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(big_full, 1);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&sml_full[i], 1); mbar_init(&sml_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&t_ready[i], AB_MATH); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&t_ready[i], AB_MATH / 32); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -231,8 +236,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (elect_one()) umma_commit(done);
     __syncwarp();
   } else {
-    // ---- math warps: two threads per query row (warp w and w+4 share a TMEM lane quadrant, 32 key columns each)
-    const int quad = warp & 3, half = warp >> 2;
+    // ---- math warps: four threads per query row (warps w, w+4, w+8, w+12 share a TMEM lane quadrant, 16 key columns each)
+    const int quad = warp & 3, part = warp >> 2;
     const int r_in = quad * 32 + lane;
     const int q_row = q0 + r_in;
     const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16);
@@ -248,24 +253,24 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(&s_full[buf], (j >> 1) & 1);
       TRACE(0, j, 1);
       tc_fence_after();
-      uint32_t s[32], d[32];
-      tmem_ld32(t_lane + TM_S + buf * 128 + half * 32, s);
-      tmem_ld32(t_lane + TM_S + buf * 128 + 64 + half * 32, d);
+      uint32_t s[AB_PC], d[AB_PC];
+      tmem_ld16(t_lane + TM_S + buf * 128 + part * AB_PC, s);
+      tmem_ld16(t_lane + TM_S + buf * 128 + 64 + part * AB_PC, d);
       tmem_ld_wait();
       TRACE(0, j, 2);
-      const int c0 = j * AB_BN + half * 32;
+      const int c0 = j * AB_BN + part * AB_PC;
       const bool need_mask = (p.causal && j * AB_BN + AB_BN - 1 > q0) || (j * AB_BN + AB_BN > p.seq_kv) || mrow;
-      uint32_t pk[16];
+      uint32_t pk[AB_PC / 2];
       if (!need_mask) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
+        for (int c = 0; c < AB_PC; c += 2) {
           const float p0 = ex2_approx(__uint_as_float(s[c]) * p.scale_log2 - lse);
           const float p1 = ex2_approx(__uint_as_float(s[c + 1]) * p.scale_log2 - lse);
           pk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(d[c]) - delta), p1 * (__uint_as_float(d[c + 1]) - delta));
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
+        for (int c = 0; c < AB_PC; c += 2) {
           float pv[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
@@ -279,34 +284,35 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
       uint8_t* sds = smem + S::OFF_T0 + buf * S::T_BYTES + r_in * 128;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch)
-        *reinterpret_cast<uint4*>(sds + (((half * 4 + ch) ^ sw) << 4)) =
+      for (int ch = 0; ch < AB_PC / 8; ++ch)
+        *reinterpret_cast<uint4*>(sds + (((part * (AB_PC / 8) + ch) ^ sw) << 4)) =
             make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
       TRACE(0, j, 3);
       fence_proxy_async();
       TRACE(0, j, 4);
       tc_fence_before();
-      mbar_arrive(&t_ready[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_ready[buf]);
       TRACE(0, j, 5);
     }
-    // ---- epilogue: the two threads of a row take alternate 32-column chunks of dQ
+    // ---- epilogue: the four threads of a row take 16-column chunks of dQ (chunk index = cc * 4 + part)
     mbar_wait(done, 0);
     tc_fence_after();
     if (n_steps > 0) {
       __nv_bfloat16* dqp = p.dq + (int64_t(b) * p.seq_q + q_row) * p.dq_row_stride + int64_t(head) * p.dq_head_stride;
 #pragma unroll
       for (int cc = 0; cc < D / 64; ++cc) {
-        const int ch = cc * 2 + half;
-        uint32_t t[32];
-        tmem_ld32(t_lane + TM_DQ + ch * 32, t);
+        const int ch = cc * AB_PARTS + part;
+        uint32_t t[AB_PC];
+        tmem_ld16(t_lane + TM_DQ + ch * AB_PC, t);
         tmem_ld_wait();
         if (row_ok) {
 #pragma unroll
-          for (int c = 0; c < 32; c += 8) {
+          for (int c = 0; c < AB_PC; c += 8) {
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(t[c + e]) * p.scale;
-            *reinterpret_cast<uint4*>(dqp + ch * 32 + c) = pack8(f);
+            *reinterpret_cast<uint4*>(dqp + ch * AB_PC + c) = pack8(f);
           }
         }
       }
@@ -345,7 +351,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   uint64_t* t_ready = s_full + 2;
   uint64_t* done = t_ready + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(done + 1);
-  float* stats = reinterpret_cast<float*>(smem + S::OFF_STATS);  // [buf][0: lse, 1: delta][64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;  // early key tiles see the most queries under a causal mask: they come first already
@@ -359,7 +364,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
     mbar_init(big_full, 1);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&sml_full[i], 1); mbar_init(&sml_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&t_ready[i], AB_MATH); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&t_ready[i], AB_MATH / 32); }
     mbar_init(done, 1);
     fence_barrier_init();
   }
@@ -454,8 +459,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     if (elect_one()) umma_commit(done);
     __syncwarp();
   } else {
-    // ---- math warps: two threads per KEY row (32 query columns each)
-    const int quad = warp & 3, half = warp >> 2;
+    // ---- math warps: four threads per KEY row (16 query columns each)
+    const int quad = warp & 3, part = warp >> 2;
     const int r_in = quad * 32 + lane;
     const int kv_row = kv0 + r_in;
     const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16);
@@ -463,40 +468,49 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     const bool store_ok = row_ok;
     if (row_ok && p.kv_mask) row_ok = p.kv_mask[int64_t(b) * p.seq_kv + kv_row] != 0;
     const int sw = r_in & 7;
-    const int tid = threadIdx.x;  // 0..255 inside the math group
     const int64_t stat_base = (int64_t(b) * p.nheads + head) * p.seq_q;
+    const bool vec_stats = (p.seq_q % 4) == 0;   // 16-byte aligned rows of lse / delta
     for (int i = 0; i < n_steps; ++i) {
       const int buf = i & 1;
       const int qt0 = (i_start + i) * AB_BN;
-      if (tid < 128) {  // stage lse / delta of this query tile (tid < 64: lse, 64..127: delta)
-        const int c = tid & 63;
-        const int qi = qt0 + c;
-        float val;
-        if (tid < 64) val = qi < p.seq_q ? p.lse[stat_base + qi] : INFINITY;
-        else val = qi < p.seq_q ? p.delta[stat_base + qi] : 0.f;
-        stats[buf * 128 + (tid < 64 ? 0 : 64) + c] = val;
+      // lse / delta of this thread's 16 query columns: same addresses in every lane (one broadcast transaction per load),
+      // issued before the wait on the tensor core so that their latency hides behind it
+      float lse_c[AB_PC], del_c[AB_PC];
+      const int qc0 = qt0 + part * AB_PC;
+      if (vec_stats && qc0 + AB_PC <= p.seq_q) {
+#pragma unroll
+        for (int c = 0; c < AB_PC; c += 4) {
+          const float4 l4 = __ldg(reinterpret_cast<const float4*>(p.lse + stat_base + qc0 + c));
+          const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.delta + stat_base + qc0 + c));
+          lse_c[c] = l4.x; lse_c[c + 1] = l4.y; lse_c[c + 2] = l4.z; lse_c[c + 3] = l4.w;
+          del_c[c] = d4.x; del_c[c + 1] = d4.y; del_c[c + 2] = d4.z; del_c[c + 3] = d4.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < AB_PC; ++c) {
+          const int qi = qc0 + c;
+          lse_c[c] = qi < p.seq_q ? __ldg(p.lse + stat_base + qi) : INFINITY;
+          del_c[c] = qi < p.seq_q ? __ldg(p.delta + stat_base + qi) : 0.f;
+        }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&s_full[buf], (i >> 1) & 1);
       tc_fence_after();
-      const float* lse_s = stats + buf * 128 + half * 32;
-      const float* del_s = lse_s + 64;
-      uint32_t s[32], d[32];
-      tmem_ld32(t_lane + TM_S + buf * 128 + half * 32, s);
-      tmem_ld32(t_lane + TM_S + buf * 128 + 64 + half * 32, d);
+      uint32_t s[AB_PC], d[AB_PC];
+      tmem_ld16(t_lane + TM_S + buf * 128 + part * AB_PC, s);
+      tmem_ld16(t_lane + TM_S + buf * 128 + 64 + part * AB_PC, d);
       tmem_ld_wait();
       const bool need_causal = p.causal && (qt0 < kv0 + AB_BM - 1);
-      uint32_t pp[16], pd[16];
+      uint32_t pp[AB_PC / 2], pd[AB_PC / 2];
 #pragma unroll
-      for (int c = 0; c < 32; c += 2) {
+      for (int c = 0; c < AB_PC; c += 2) {
         float pv[2], dv[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          float x = ex2_approx(__uint_as_float(s[c + e]) * p.scale_log2 - lse_s[c + e]);
-          const bool keep = row_ok && !(need_causal && (qt0 + half * 32 + c + e) < kv_row);
+          float x = ex2_approx(__uint_as_float(s[c + e]) * p.scale_log2 - lse_c[c + e]);
+          const bool keep = row_ok && !(need_causal && (qc0 + c + e) < kv_row);
           x = keep ? x : 0.f;
           pv[e] = x;
-          dv[e] = x * (__uint_as_float(d[c + e]) - del_s[c + e]);
+          dv[e] = x * (__uint_as_float(d[c + e]) - del_c[c + e]);
         }
         pp[c >> 1] = pack_bf16x2(pv[0], pv[1]);
         pd[c >> 1] = pack_bf16x2(dv[0], dv[1]);
@@ -504,17 +518,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       uint8_t* spt = smem + S::OFF_T0 + buf * S::T_BYTES + r_in * 128;
       uint8_t* sdst = smem + S::OFF_T1 + buf * S::T_BYTES + r_in * 128;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        *reinterpret_cast<uint4*>(spt + (((half * 4 + ch) ^ sw) << 4)) =
+      for (int ch = 0; ch < AB_PC / 8; ++ch) {
+        *reinterpret_cast<uint4*>(spt + (((part * (AB_PC / 8) + ch) ^ sw) << 4)) =
             make_uint4(pp[ch * 4], pp[ch * 4 + 1], pp[ch * 4 + 2], pp[ch * 4 + 3]);
-        *reinterpret_cast<uint4*>(sdst + (((half * 4 + ch) ^ sw) << 4)) =
+        *reinterpret_cast<uint4*>(sdst + (((part * (AB_PC / 8) + ch) ^ sw) << 4)) =
             make_uint4(pd[ch * 4], pd[ch * 4 + 1], pd[ch * 4 + 2], pd[ch * 4 + 3]);
       }
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&t_ready[buf]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_ready[buf]);
     }
-    // ---- epilogue: dV, dK; the two threads of a row take alternate 32-column chunks
+    // ---- epilogue: dV, dK; the four threads of a row take 16-column chunks (chunk index = cc * 4 + part)
     mbar_wait(done, 0);
     tc_fence_after();
     __nv_bfloat16* dvp = p.dv + (int64_t(b) * p.seq_kv + kv_row) * p.dv_row_stride + int64_t(head) * p.dv_head_stride;
@@ -523,20 +538,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     for (int which = 0; which < 2; ++which) {
 #pragma unroll
       for (int cc = 0; cc < D / 64; ++cc) {
-        const int ch = cc * 2 + half;
-        uint32_t t[32];
+        const int ch = cc * AB_PARTS + part;
+        uint32_t t[AB_PC];
         if (n_steps > 0) {
-          tmem_ld32(t_lane + (which == 0 ? TM_DV : TM_DK) + ch * 32, t);
+          tmem_ld16(t_lane + (which == 0 ? TM_DV : TM_DK) + ch * AB_PC, t);
           tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) t[c] = 0u;
+          for (int c = 0; c < AB_PC; ++c) t[c] = 0u;
         }
         if (store_ok) {
           const float mul = which == 0 ? 1.f : p.scale;
-          __nv_bfloat16* dst = (which == 0 ? dvp : dkp) + ch * 32;
+          __nv_bfloat16* dst = (which == 0 ? dvp : dkp) + ch * AB_PC;
 #pragma unroll
-          for (int c = 0; c < 32; c += 8) {
+          for (int c = 0; c < AB_PC; c += 8) {
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(t[c + e]) * mul;
