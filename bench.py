@@ -77,6 +77,19 @@ def flops_per_token(w):
     return 6.0 * n_mm + 3.0 * attn
 
 
+# DRAM traffic of the dominant kernel's largest-share launch, from the committed `ncu --set full` capture
+# (profiles/r01_ncu_gemm_v3.summary.txt; dram__bytes_read.sum + dram__bytes_write.sum, one launch), next to its algorithmic
+# bytes (A + B read once, D written once). bench.py cannot run ncu itself, so these are constants tied to that capture.
+NCU_TRAFFIC = {
+    "gpt2": {"launch": "fsb::gemm_bf16_kernel NN 32768x3072x768 (c_fc forward)", "traffic": 55.156224e6 + 144.0e6,
+             "algorithmic": (32768 * 768 + 768 * 3072 + 32768 * 3072) * 2.0,
+             "source": "profiles/r01_ncu_gemm_v3.summary.txt"},
+    "llama": {"launch": "fsb::gemm_bf16_kernel NT 8192x15360x5120 (QKV forward)", "traffic": 584.21e6 + 236.86e6,
+              "algorithmic": (8192 * 5120 + 15360 * 5120 + 8192 * 15360) * 2.0,
+              "source": "profiles/r01_ncu_gemm_v3.summary.txt (after the rasterisation change; 1379 MB + 239 MB before)"},
+}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -399,7 +412,9 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": cfg_common,
             "roofline": {"bound": "tensor", "kernel": "fsb::gemm_bf16_kernel (tcgen05)", "achieved": gemm_tf,
                          "peak": pk["bf16_tflops"], "unit": "TFLOP/s", "frac": gemm_tf / pk["bf16_tflops"],
-                         "traffic": None, "peak_source": pk["src"], "launches_per_step": gsum["launches"] / args.steps,
+                         "traffic": (NCU_TRAFFIC.get(w["family"]) or {}).get("traffic"),
+                         "traffic_detail": NCU_TRAFFIC.get(w["family"]),
+                         "peak_source": pk["src"], "launches_per_step": gsum["launches"] / args.steps,
                          "kernel_share_of_step": gsum["ms"] / ms if ms > 0 else None,
                          "step_achieved_tflops_per_gpu": step_tf, "step_frac": step_tf / pk["bf16_tflops"]},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss}
