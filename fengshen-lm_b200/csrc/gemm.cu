@@ -12,6 +12,8 @@
 // quadrant = warp_id % 4, and the two warps of a quadrant split the tile's 64-column groups between them (bias /
 // activation / bf16 conversion are instruction-bound with one warp per scheduler). Two TMEM accumulator stages let the
 // epilogue of tile i overlap the main loop of tile i+1. Grid = min(#tiles, #SMs); static round-robin tile order, grouped 8 m-tiles deep for L2.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -21,6 +23,9 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARP0 = 4;   // first epilogue warp
+#ifndef FSB_GEMM_CTA2_DEFAULT
+#define FSB_GEMM_CTA2_DEFAULT true
+#endif
 
 struct GemmParams {
   void* D;
@@ -40,12 +45,16 @@ struct GemmParams {
 // kAux: the GEMM also writes the pre-activation (GELU MLPs): two bulk stores per column group. Their smem->global reads
 // queue behind the mainloop's TMA loads, so that variant trades one operand stage (K is the hidden size there, short
 // mainloops) for a four-deep staging ring per epilogue warp.
-template <int BN, bool kAux>
+// kCta2: CTA-pair variant (tcgen05 cta_group::2): the pair computes a 256 x BN tile; each CTA stages its own 128 rows of A and
+// HALF of B (BN/2 columns), so a stage is 32 KB instead of 48 KB and the per-SM shared-memory traffic (TMA fill + MMA operand
+// reads: 192 B/clk for a lone 128x256 tile, above the 128 B/clk an SM delivers) drops to 128 B/clk.
+template <int BN, bool kAux, bool kCta2>
 struct GemmSmem {
-  static constexpr int STAGES = BN == 256 ? (kAux ? 3 : 4) : (kAux ? 5 : 6);
+  static constexpr int BNL = kCta2 ? BN / 2 : BN;                  // B columns staged by this CTA
+  static constexpr int STAGES = kCta2 ? (kAux ? 5 : 6) : BN == 256 ? (kAux ? 3 : 4) : (kAux ? 5 : 6);
   static constexpr int NBUF = kAux ? 4 : 2;                        // staging tiles per epilogue warp
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int B_BYTES = BNL * GEMM_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STORE_OFFSET = STAGES * STAGE_BYTES;       // per epilogue warp: NBUF x [32 rows x 64 cols] bf16 staging tiles
   static constexpr int STORE_WARP_BYTES = 32 * 64 * 2;
@@ -91,16 +100,21 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
   n_idx = in_g / gsize;
 }
 
-template <int kLayout, int BN, bool kAux>
+template <int kLayout, int BN, bool kAux, bool kCta2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmAux, const GemmParams p) {
   constexpr bool A_MN = (kLayout == FSB_GEMM_TN);
   constexpr bool B_MN = (kLayout != FSB_GEMM_NT);
-  using S = GemmSmem<BN, kAux>;
+  using S = GemmSmem<BN, kAux, kCta2>;
   constexpr int STAGES = S::STAGES;
-  constexpr uint32_t IDESC = make_idesc_bf16(GEMM_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+  constexpr int BNL = S::BNL;
+  constexpr int TILE_M = kCta2 ? 2 * GEMM_BM : GEMM_BM;   // rows of one (cluster) tile
+  constexpr uint32_t IDESC = make_idesc_bf16(TILE_M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
   constexpr int TMEM_COLS = 2 * BN;  // 512 or 256
+  const uint32_t cta_rank = kCta2 ? cluster_ctarank() : 0u;        // 0 = leader (issues the pair's MMAs)
+  const int tile_first = kCta2 ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int tile_step = kCta2 ? int(gridDim.x >> 1) : int(gridDim.x);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -124,13 +138,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], p.tma_store ? 8 : 4);  // one arrive per participating epilogue warp
+      mbar_init(&tmem_empty[i], (p.tma_store ? 8 : 4) * (kCta2 ? 2 : 1));  // one arrive per participating epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  if (warp == 1) {
+    if constexpr (kCta2) tmem_alloc_2cta<TMEM_COLS>(tmem_ptr_smem); else tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCta2) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -140,29 +157,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      // (pair) both CTAs load their own halves; every transaction is credited to the LEADER's full barrier, on which the
+      // leader alone posts the expected byte count of the whole pair
+      auto load = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+        if constexpr (kCta2) tma_load_3d_2cta(dst, tm, mapa_shared(smem_u32(bar), 0), c0, c1, c2);
+        else tma_load_3d(dst, tm, bar, c0, c1, c2);
+      };
+      for (int t = tile_first; t < num_tiles; t += tile_step) {
         int b, m_idx, n_idx;
         tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, b, m_idx, n_idx);
-        const int m0 = m_idx * GEMM_BM, n0 = n_idx * BN;
+        const int m0 = m_idx * TILE_M + int(cta_rank) * GEMM_BM, n0 = n_idx * BN + int(cta_rank) * (kCta2 ? BNL : 0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          if (!kCta2 || cta_rank == 0) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES * (kCta2 ? 2 : 1));
           const int k0 = kb * GEMM_BK;
           if constexpr (!A_MN) {
-            tma_load_3d(sa, &tmA, &full_bar[stage], k0, m0, b);
+            load(sa, &tmA, &full_bar[stage], k0, m0, b);
           } else {
 #pragma unroll
             for (int c = 0; c < GEMM_BM / 64; ++c)
-              tma_load_3d(sa + c * (GEMM_BK * 128), &tmA, &full_bar[stage], m0 + c * 64, k0, b);
+              load(sa + c * (GEMM_BK * 128), &tmA, &full_bar[stage], m0 + c * 64, k0, b);
           }
           if constexpr (!B_MN) {
-            tma_load_3d(sb, &tmB, &full_bar[stage], k0, n0, b);
+            load(sb, &tmB, &full_bar[stage], k0, n0, b);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_3d(sb + c * (GEMM_BK * 128), &tmB, &full_bar[stage], n0 + c * 64, k0, b);
+            for (int c = 0; c < BNL / 64; ++c)
+              load(sb + c * (GEMM_BK * 128), &tmB, &full_bar[stage], n0 + c * 64, k0, b);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -179,7 +202,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    if (!kCta2 || cta_rank == 0)   // (pair) the leader issues for both SMs; commits are multicast to both CTAs' barriers
+    for (int t = tile_first; t < num_tiles; t += tile_step) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -189,15 +213,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (elect_one()) {
           const uint64_t so = uint64_t(stage) * (S::STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            umma_bf16(d_tmem, dsc_a + so + ((A_MN ? k * 2048 : k * 32) >> 4), dsc_b + so + ((B_MN ? k * 2048 : k * 32) >> 4),
-                      IDESC, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs retire
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t da = dsc_a + so + ((A_MN ? k * 2048 : k * 32) >> 4), db = dsc_b + so + ((B_MN ? k * 2048 : k * 32) >> 4);
+            if constexpr (kCta2) umma_bf16_2cta(d_tmem, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          // frees this smem stage (in both CTAs) when the MMAs retire
+          if constexpr (kCta2) umma_commit_2cta(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      if (elect_one()) umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+      if (elect_one()) {   // accumulator ready for the epilogue (of both CTAs)
+        if constexpr (kCta2) umma_commit_2cta(&tmem_full[acc], 3); else umma_commit(&tmem_full[acc]);
+      }
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -210,6 +239,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int half = (warp - GEMM_EPI_WARP0) >> 2;    // which of the quadrant's two warps
     int acc = 0;
     uint32_t acc_phase = 0;
+    // hand an accumulator stage back to the MMA warp (the pair's leader owns the barrier)
+    auto release_acc = [&](int a) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (kCta2 && cta_rank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty[a]), 0));
+        else mbar_arrive(&tmem_empty[a]);
+      }
+    };
     if (p.tma_store) {
       // ---- bf16 D without accumulate (forward / dgrad GEMMs): every warp owns its 32 rows end to end.
       // TMEM -> registers 64 columns at a time (the next group's tcgen05.ld is in flight while this one is converted),
@@ -235,10 +273,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         ++item;
       };
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = tile_first; t < num_tiles; t += tile_step) {
         int b, m_idx, n_idx;
         tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, b, m_idx, n_idx);
-        const int r0 = m_idx * GEMM_BM + quad * 32;
+        const int r0 = m_idx * TILE_M + int(cta_rank) * GEMM_BM + quad * 32;
         const int n0 = n_idx * BN;
         constexpr int NG = BN / 64;
         const int ng = min(NG, (p.N - n0 + 63) / 64);     // column groups of this tile that exist
@@ -247,9 +285,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t t_acc = tmem_base + (uint32_t(quad * 32) << 16) + acc * BN;
         constexpr int NGW = NG / 2;                        // column groups per warp: g = 2 * i + half
         if (half >= ng) {                                  // (ragged last tile) nothing for this warp: just release
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          release_acc(acc);
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
           continue;
         }
@@ -285,9 +321,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tmem_ld32_at<0>(t_acc + (g + 2) * 64, r[(i + 1) & 1]);
               tmem_ld32_at<32>(t_acc + (g + 2) * 64 + 32, r[(i + 1) & 1]);
             } else {                                       // last read of this accumulator: give it back to the MMA warp
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+              release_acc(acc);
             }
             uint32_t (&v)[64] = r[i & 1];
             const int col0 = n0 + g * 64;
@@ -329,10 +363,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (lane == 0) tma_store_wait_read<0>();     // smem must outlive the last bulk stores' reads
     } else if (half == 0)
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = tile_first; t < num_tiles; t += tile_step) {
       int b, m_idx, n_idx;
       tile_coords(t, p.tiles_m, p.tiles_n, p.group_m, b, m_idx, n_idx);
-      const int row = m_idx * GEMM_BM + quad * 32 + lane;
+      const int row = m_idx * TILE_M + int(cta_rank) * GEMM_BM + quad * 32 + lane;
       const int n0 = n_idx * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -421,27 +455,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      release_acc(acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCta2) cluster_sync_all();   // the peer may still be reading TMEM / signalling our barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if constexpr (kCta2) tmem_dealloc_2cta<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
-template <int kLayout, int BN, bool kAux>
+template <int kLayout, int BN, bool kAux, bool kCta2>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAux,
                        const GemmParams& p, cudaStream_t stream) {
-  using S = GemmSmem<BN, kAux>;
+  using S = GemmSmem<BN, kAux, kCta2>;
   static bool configured = false;
-  auto kern = gemm_bf16_kernel<kLayout, BN, kAux>;
+  auto kern = gemm_bf16_kernel<kLayout, BN, kAux, kCta2>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) {
@@ -451,8 +484,26 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
     configured = true;
   }
   const int num_tiles = p.tiles_m * p.tiles_n * p.batch;
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmD, tmAux, p);
+  if constexpr (kCta2) {
+    const int pairs = num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (num_tiles < pairs ? num_tiles : pairs));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmAux, p);
+    if (e != cudaSuccess) {
+      set_error("gemm: cluster launch failed: %s", cudaGetErrorString(e));
+      return FSB_ERR_CUDA;
+    }
+  } else {
+    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmD, tmAux, p);
+  }
   FSB_CUDA_LAUNCH_CHECK();
   return FSB_OK;
 }
@@ -502,7 +553,7 @@ static float* splitk_workspace(size_t bytes) {
 static int gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                      int64_t ldb, void* D, int64_t ldd, int d_dtype, const void* bias, int bias_dtype,
                      int epilogue, int accumulate, void* aux, int64_t ldaux, int64_t batch, int64_t stride_a,
-                     int64_t stride_b, int64_t stride_d, int64_t stride_aux, cudaStream_t stream);
+                     int64_t stride_b, int64_t stride_d, int64_t stride_aux, cudaStream_t stream, bool force_pair = false);
 
 }  // namespace fsb
 
@@ -517,16 +568,20 @@ extern "C" int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K, const 
   // run `splits` K-chunks as a batched GEMM into an fp32 scratch, then sum the chunks in a fixed order (deterministic).
   if (layout == FSB_GEMM_TN && batch == 1 && bias == nullptr && aux == nullptr && epilogue == FSB_EPI_NONE && M > 0 &&
       N > 0 && N % 4 == 0 && (M * N) % 8 == 0 && K >= 4096 && (d_dtype == FSB_BF16 || d_dtype == FSB_F32)) {
-    const int64_t tiles = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + 127) / 128);
-    int splits = int(num_sms() / tiles);
+    // Preferred: 256 x 256 CTA-pair tiles (a lone 128 x 128 tile is shared-memory-bound at half the MMA rate), K split so
+    // that the SM pairs are busy; small outputs (M or N < 256) keep 128 x 128 tiles.
+    const bool pair = M >= 256 && N >= 256;
+    const int64_t tiles = pair ? ((M + 255) / 256) * ((N + 255) / 256) : ((M + GEMM_BM - 1) / GEMM_BM) * ((N + 127) / 128);
+    const int64_t slots = pair ? num_sms() / 2 : num_sms();
+    int splits = int(slots / tiles);
     if (splits > 16) splits = 16;
     while (splits > 1 && (K % (int64_t(splits) * GEMM_BK) != 0 || K / splits < 1024)) --splits;
-    if (splits >= 2 && tiles * 2 <= num_sms()) {
+    if (splits >= 2 && tiles * 2 <= slots) {
       float* ws = splitk_workspace(size_t(splits) * M * N * sizeof(float));
       if (ws == nullptr) { set_error("gemm: cannot allocate the split-K scratch (%zu bytes)", size_t(splits) * M * N * 4); return FSB_ERR_CUDA; }
       const int64_t kc = K / splits;
       int rc = gemm_impl(layout, M, N, kc, A, lda, B, ldb, ws, N, FSB_F32, nullptr, FSB_BF16, FSB_EPI_NONE, 0, nullptr, 0,
-                         splits, kc * lda, kc * ldb, M * N, 0, stream);
+                         splits, kc * lda, kc * ldb, M * N, 0, stream, pair);
       if (rc) return rc;
       FSB_REQUIRE(ldd % 4 == 0, "gemm: ldd=%ld not vector-aligned", (long)ldd);
       const int64_t work = M * (N / 4);
@@ -543,7 +598,7 @@ extern "C" int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K, const 
 static int fsb::gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                           int64_t ldb, void* D, int64_t ldd, int d_dtype, const void* bias, int bias_dtype,
                           int epilogue, int accumulate, void* aux, int64_t ldaux, int64_t batch, int64_t stride_a,
-                          int64_t stride_b, int64_t stride_d, int64_t stride_aux, cudaStream_t stream) {
+                          int64_t stride_b, int64_t stride_d, int64_t stride_aux, cudaStream_t stream, bool force_pair) {
   FSB_REQUIRE(layout >= 0 && layout <= 2, "gemm: bad layout %d", layout);
   FSB_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0, "gemm: non-positive dims M=%ld N=%ld K=%ld batch=%ld", (long)M,
               (long)N, (long)K, (long)batch);
@@ -565,7 +620,10 @@ static int fsb::gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const voi
   // 128 x 256 tiles unless they would leave a large part of the 148 SMs idle (weight-gradient GEMMs of small models:
   // e.g. 768 x 2304 x 32768 is only 54 such tiles) — then 128 x 128 tiles double the parallelism.
   const int64_t tiles256 = ((M + GEMM_BM - 1) / GEMM_BM) * ((N + 255) / 256) * batch;
-  const int BN = (N > 128 && tiles256 * 10 >= int64_t(num_sms()) * 7) ? 256 : 128;
+  const int BN = (force_pair || (N > 128 && tiles256 * 10 >= int64_t(num_sms()) * 7)) ? 256 : 128;
+  // CTA pairs (cta_group::2, 256 x 256 tiles) once there is at least one pair tile per SM pair; FSB_GEMM_CTA2=0/1 overrides.
+  static const int cta2_env = [] { const char* e = getenv("FSB_GEMM_CTA2"); return e ? atoi(e) : -1; }();
+  const bool cta2 = force_pair || (BN == 256 && tiles256 >= num_sms() && (cta2_env < 0 ? FSB_GEMM_CTA2_DEFAULT : cta2_env != 0));
   {
     // A: K-major -> memory [M rows, K inner]; MN-major -> memory [K rows, M inner]
     uint64_t dims[3] = {uint64_t(a_mn ? M : K), uint64_t(a_mn ? K : M), uint64_t(batch)};
@@ -577,7 +635,7 @@ static int fsb::gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const voi
   {
     uint64_t dims[3] = {uint64_t(b_mn ? N : K), uint64_t(b_mn ? K : N), uint64_t(batch)};
     uint64_t strides[2] = {uint64_t(ldb) * 2, uint64_t(batch > 1 ? stride_b : (b_mn ? K : N) * ldb) * 2};
-    uint32_t box[3] = {64, uint32_t(b_mn ? GEMM_BK : BN), 1};
+    uint32_t box[3] = {64, uint32_t(b_mn ? GEMM_BK : (cta2 ? BN / 2 : BN)), 1};
     int rc = make_tmap_bf16(&tmB, B, 3, dims, strides, box);
     if (rc) return rc;
   }
@@ -601,7 +659,7 @@ static int fsb::gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const voi
   p.M = int(M); p.N = int(N); p.K = int(K); p.batch = int(batch);
   p.d_f32 = (d_dtype == FSB_F32); p.bias_f32 = (bias_dtype == FSB_F32);
   p.epilogue = epilogue; p.accumulate = accumulate;
-  p.tiles_m = int((M + GEMM_BM - 1) / GEMM_BM);
+  p.tiles_m = cta2 ? int((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) : int((M + GEMM_BM - 1) / GEMM_BM);
   p.tiles_n = int((N + BN - 1) / BN);
   // Rasterisation: tiles are walked m-fastest inside groups of group_m m-tiles, so one wave of CTAs touches group_m A panels
   // and #SMs/group_m B panels. HBM traffic per wave is minimal when both sides weigh the same (group_m ~ sqrt(#SMs * BN/BM):
@@ -613,16 +671,19 @@ static int fsb::gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const voi
     const int64_t base = BN == 256 ? 16 : 12;
     int64_t gm = (int64_t(32) << 20) / a_panel;
     gm = gm < base ? base : (gm > 64 ? 64 : gm);
-    p.group_m = int(gm);
+    p.group_m = cta2 ? int((gm + 1) / 2) : int(gm);   // pair tiles are two A panels tall
   }
 
 #define FSB_GEMM_DISPATCH(L)                                                    \
   case L:                                                                        \
+    if (cta2)                                                                                                    \
+      return (p.tma_store && aux != nullptr) ? launch_gemm<L, 256, true, true>(tmA, tmB, tmD, tmAux, p, stream)   \
+                                             : launch_gemm<L, 256, false, true>(tmA, tmB, tmD, tmAux, p, stream); \
     if (p.tma_store && aux != nullptr)                                                                           \
-      return BN == 256 ? launch_gemm<L, 256, true>(tmA, tmB, tmD, tmAux, p, stream)                               \
-                       : launch_gemm<L, 128, true>(tmA, tmB, tmD, tmAux, p, stream);                              \
-    return BN == 256 ? launch_gemm<L, 256, false>(tmA, tmB, tmD, tmAux, p, stream)                                \
-                     : launch_gemm<L, 128, false>(tmA, tmB, tmD, tmAux, p, stream);
+      return BN == 256 ? launch_gemm<L, 256, true, false>(tmA, tmB, tmD, tmAux, p, stream)                        \
+                       : launch_gemm<L, 128, true, false>(tmA, tmB, tmD, tmAux, p, stream);                       \
+    return BN == 256 ? launch_gemm<L, 256, false, false>(tmA, tmB, tmD, tmAux, p, stream)                         \
+                     : launch_gemm<L, 128, false, false>(tmA, tmB, tmD, tmAux, p, stream);
   switch (layout) {
     FSB_GEMM_DISPATCH(FSB_GEMM_NT)
     FSB_GEMM_DISPATCH(FSB_GEMM_NN)

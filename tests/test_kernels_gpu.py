@@ -90,6 +90,35 @@ def test_gemm_splitk_wgrad():
     assert torch.equal(out, again), "split-K must be deterministic"
 
 
+@pytest.mark.parametrize("layout", [L.GEMM_NT, L.GEMM_NN, L.GEMM_TN])
+def test_gemm_cta_pair_tiles(layout):
+    """Shapes with >= one 256x256 tile per SM pair run the cta_group::2 kernel; ragged M / N edges, every epilogue."""
+    M, N, K = 2304 + 40, 4096 + 72, 320          # 10 x 17 pair tiles, both edges ragged (TMA zero-fill / clipped stores)
+    if layout == L.GEMM_NT:
+        a, b = _rand(M, K, seed=11), _rand(N, K, seed=12, scale=0.1)
+        ref = a.float() @ b.float().t()
+    elif layout == L.GEMM_NN:
+        a, b = _rand(M, K, seed=11), _rand(K, N, seed=12, scale=0.1)
+        ref = a.float() @ b.float()
+    else:
+        a, b = _rand(K, M, seed=11), _rand(K, N, seed=12, scale=0.1)
+        ref = a.float().t() @ b.float()
+    out = ops.gemm(layout, a, b)
+    _close(out, ref, atol=2e-2 * math.sqrt(K / 64), rtol=1e-2, what="pair-tile bf16")
+    bias = _rand(N, seed=13)
+    aux = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    out = ops.gemm(layout, a, b, bias=bias, epilogue=L.EPI_GELU_TANH, aux=aux)
+    pre = ref + bias.float()
+    _close(aux, pre, 3e-2, 1e-2, "pair-tile aux")
+    _close(out, torch.nn.functional.gelu(pre, approximate="tanh"), 3e-2, 1e-2, "pair-tile gelu")
+    acc = torch.full((M, N), 0.5, dtype=torch.float32, device=DEV)
+    ops.gemm(layout, a, b, out=acc, accumulate=True)
+    _close(acc, ref + 0.5, atol=1e-3 * math.sqrt(K / 64), rtol=1e-4, what="pair-tile fp32 accumulate")
+    accb = torch.ones(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(layout, a, b, out=accb, accumulate=True)
+    _close(accb, ref + 1.0, atol=3e-2 * math.sqrt(K / 64), rtol=1e-2, what="pair-tile bf16 accumulate")
+
+
 def test_gemm_rejects_bad_arguments():
     a = _rand(64, 60)  # lda = 60 not a multiple of 8
     b = _rand(64, 60)
