@@ -8,11 +8,9 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 csrc = os.path.join(ROOT, "fengshen-lm_b200", "csrc")
-out = "/tmp/libfsb200_trace.so"
-srcs = [os.path.join(csrc, f) for f in
-        "host_common.cu gemm.cu norm.cu elementwise.cu loss_optim.cu attention_fwd.cu attention_bwd.cu softmax.cu".split()]
-subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DFSB_ATTN_TRACE",
-                "--compiler-options", "-fPIC", "-shared", "-o", out, "-cudart", "static"] + srcs, check=True)
+out = os.path.join(ROOT, "fengshen-lm_b200", "build", "libfsb200_trace.so")   # build it on the CPU box: make -C csrc trace
+if not os.path.exists(out):
+    raise SystemExit("build the traced library first: make -C fengshen-lm_b200/csrc trace")
 sys.path.insert(0, os.path.join(ROOT, "fengshen-lm_b200"))
 from fsb200 import lib  # noqa: E402
 lib.LIB_PATH = out
