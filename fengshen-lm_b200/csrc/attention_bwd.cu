@@ -35,6 +35,8 @@ struct AttBwdParams {
   const float* lse;     // [B,H,Sq] log2 domain
   const float* delta;   // [B,H,Sq]
   const uint8_t* kv_mask;
+  const __nv_bfloat16 *q, *dout, *k, *v;   // raw views: at D = 64 each math thread parks its own Q / dO (dQ kernel) or K / V (dKV kernel) row in TMEM as MMA A operands
+  int64_t q_row_stride, do_row_stride, k_row_stride, v_row_stride;
   __nv_bfloat16 *dq, *dk, *dv;
   int64_t dq_row_stride, dk_row_stride, dv_row_stride, dq_head_stride, dk_head_stride, dv_head_stride;
   int q_head_stride, k_head_stride, v_head_stride, do_head_stride;
@@ -110,8 +112,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   using S = AttBwdSmem<D, (D == 64 ? 6 : 4), 2>;
   constexpr int STAGES = S::STAGES;
   constexpr int TMEM_COLS = 512;
+  // All three products take their A operand from TENSOR MEMORY (row == lane, bf16 pairs per 32-bit column), so the tensor
+  // core only streams the K / V tiles from shared memory (an SS-mode 128x64x16 MMA reads 6 KB per 32 cycles — 192 B/clk
+  // against the 128 B/clk an SM's shared memory delivers; with A in TMEM it is 2 KB):
+  //   Q, dO : parked once per CTA by the math threads (each thread loads its own row slice from global)
+  //   dS(j) : written by the math threads over the S(j) columns they have just consumed (part p -> columns 16p..16p+7)
   constexpr int TM_S = 0;     // S[buf] at buf*128, dP[buf] at buf*128 + 64
   constexpr int TM_DQ = 256;  // D columns
+  constexpr bool kQT = (D == 64);          // Q / dO as TMEM operands: measured -16 % per step at D = 64, +4 % at D = 128 (kept in smem there)
+  constexpr int TM_Q = 256 + D;            // D/2 columns
+  constexpr int TM_DO = 256 + D + D / 2;   // D/2 columns  (256 + 2 D <= 512)
   constexpr uint32_t IDESC_S = make_idesc_bf16(AB_BM, AB_BN, 0, 0);
   constexpr uint32_t IDESC_DQ = make_idesc_bf16(AB_BM, D, 0, 1);
 
@@ -139,7 +149,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == AB_W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    mbar_init(big_full, 1);
+    mbar_init(big_full, kQT ? AB_MATH / 32 : 1);   // Q / dO parked in TMEM (one arrival per math warp) or loaded by TMA
     for (int i = 0; i < STAGES; ++i) { mbar_init(&sml_full[i], 1); mbar_init(&sml_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&t_ready[i], AB_MATH / 32); }
     mbar_init(done, 1);
@@ -153,13 +163,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (warp == AB_W_TMA) {
     if (lane == 0) {
-      const int qc = head * p.q_head_stride, dc = head * p.do_head_stride;
       const int kc = head * p.k_head_stride, vc = head * p.v_head_stride;
-      mbar_expect_tx(big_full, 2 * S::BIG_BYTES);
+      if constexpr (!kQT) {
+        const int qc = head * p.q_head_stride, dc = head * p.do_head_stride;
+        mbar_expect_tx(big_full, 2 * S::BIG_BYTES);
 #pragma unroll
-      for (int h = 0; h < D / 64; ++h) {
-        tma_load_3d(smem + S::OFF_BIG0 + h * (AB_BM * 128), &tmQ, big_full, qc + h * 64, q0, b);
-        tma_load_3d(smem + S::OFF_BIG1 + h * (AB_BM * 128), &tmdO, big_full, dc + h * 64, q0, b);
+        for (int h = 0; h < D / 64; ++h) {
+          tma_load_3d(smem + S::OFF_BIG0 + h * (AB_BM * 128), &tmQ, big_full, qc + h * 64, q0, b);
+          tma_load_3d(smem + S::OFF_BIG1 + h * (AB_BM * 128), &tmdO, big_full, dc + h * 64, q0, b);
+        }
       }
       int st = 0; uint32_t ph = 0;
       for (int j = 0; j < n_steps; ++j) {
@@ -182,25 +194,27 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint64_t dsc_k = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML0), 0, 1024);          // K-major view (S)
     const uint64_t dsc_v = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML1), 0, 1024);
     const uint64_t dsc_kmn = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML0), AB_BN * 128, 1024);  // MN-major view (dQ)
-    const uint64_t dsc_ds = make_smem_desc_sw128(smem_u32(smem + S::OFF_T0), 0, 1024);
     auto issue_s_dp = [&](int buf, int st) {
       if (elect_one()) {
         const uint64_t sto = uint64_t(st) * (S::SML_BYTES >> 4);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t oa = ((kk / 4) * (AB_BM * 128) + (kk % 4) * 32) >> 4, ob = ((kk / 4) * (AB_BN * 128) + (kk % 4) * 32) >> 4;
-          umma_bf16(tmem_base + TM_S + buf * 128, dsc_q + oa, dsc_k + sto + ob, IDESC_S, kk != 0);
+          if constexpr (kQT) umma_bf16_ts(tmem_base + TM_S + buf * 128, tmem_base + TM_Q + kk * 8, dsc_k + sto + ob, IDESC_S, kk != 0);
+          else umma_bf16(tmem_base + TM_S + buf * 128, dsc_q + oa, dsc_k + sto + ob, IDESC_S, kk != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t oa = ((kk / 4) * (AB_BM * 128) + (kk % 4) * 32) >> 4, ob = ((kk / 4) * (AB_BN * 128) + (kk % 4) * 32) >> 4;
-          umma_bf16(tmem_base + TM_S + buf * 128 + 64, dsc_do + oa, dsc_v + sto + ob, IDESC_S, kk != 0);
+          if constexpr (kQT) umma_bf16_ts(tmem_base + TM_S + buf * 128 + 64, tmem_base + TM_DO + kk * 8, dsc_v + sto + ob, IDESC_S, kk != 0);
+          else umma_bf16(tmem_base + TM_S + buf * 128 + 64, dsc_do + oa, dsc_v + sto + ob, IDESC_S, kk != 0);
         }
         umma_commit(&s_full[buf]);
       }
       __syncwarp();
     };
-    mbar_wait(big_full, 0);
+    mbar_wait(big_full, 0);   // Q and dO rows are in TMEM
+    tc_fence_after();
     if (n_steps > 0) {
       mbar_wait(&sml_full[0], 0);
       tc_fence_after();
@@ -222,11 +236,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       TRACE(1, j, 3);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t da = dsc_ds + uint64_t(j & 1) * (S::T_BYTES >> 4);
         const uint64_t db = dsc_kmn + uint64_t(st) * (S::SML_BYTES >> 4);
 #pragma unroll
-        for (int kk = 0; kk < AB_BN / 16; ++kk)
-          umma_bf16(tmem_base + TM_DQ, da + ((kk * 32) >> 4), db + ((kk * 2048) >> 4), IDESC_DQ, (j | kk) != 0);
+        for (int kk = 0; kk < AB_BN / 16; ++kk)   // dS(j): key slice kk sits where column part kk read its S values
+          umma_bf16_ts(tmem_base + TM_DQ, tmem_base + TM_S + (j & 1) * 128 + 16 * kk, db + ((kk * 2048) >> 4), IDESC_DQ,
+                       (j | kk) != 0);
         umma_commit(&sml_empty[st]);
       }
       __syncwarp();
@@ -246,7 +260,26 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float lse = row_ok ? p.lse[stat_idx] : INFINITY;
     const float delta = row_ok ? p.delta[stat_idx] : 0.f;
     const uint8_t* mrow = p.kv_mask ? p.kv_mask + int64_t(b) * p.seq_kv : nullptr;
-    const int sw = r_in & 7;
+    if constexpr (kQT) {  // park this thread's quarter of its Q and dO rows in TMEM (bf16 pairs, column = d / 2): the A operands of S and dP
+      constexpr int W = D / 2 / AB_PARTS;   // 32-bit words per thread: 8 (D = 64) or 16 (D = 128)
+      uint32_t wq[W], wd[W];
+      const uint4* gq = reinterpret_cast<const uint4*>(p.q + (int64_t(b) * p.seq_q + q_row) * p.q_row_stride +
+                                                       int64_t(head) * p.q_head_stride + part * (2 * W));
+      const uint4* gd = reinterpret_cast<const uint4*>(p.dout + (int64_t(b) * p.seq_q + q_row) * p.do_row_stride +
+                                                       int64_t(head) * p.do_head_stride + part * (2 * W));
+#pragma unroll
+      for (int i = 0; i < W / 4; ++i) {
+        const uint4 a = row_ok ? gq[i] : make_uint4(0, 0, 0, 0), c = row_ok ? gd[i] : make_uint4(0, 0, 0, 0);
+        wq[4 * i] = a.x; wq[4 * i + 1] = a.y; wq[4 * i + 2] = a.z; wq[4 * i + 3] = a.w;
+        wd[4 * i] = c.x; wd[4 * i + 1] = c.y; wd[4 * i + 2] = c.z; wd[4 * i + 3] = c.w;
+      }
+      if constexpr (W == 8) { tmem_st8(t_lane + TM_Q + part * W, wq); tmem_st8(t_lane + TM_DO + part * W, wd); }
+      else { tmem_st16(t_lane + TM_Q + part * W, wq); tmem_st16(t_lane + TM_DO + part * W, wd); }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(big_full);
+    }
     for (int j = 0; j < n_steps; ++j) {
       const int buf = j & 1;
       TRACE(0, j, 0);
@@ -282,13 +315,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           pk[c >> 1] = pack_bf16x2(pv[0] * (__uint_as_float(d[c]) - delta), pv[1] * (__uint_as_float(d[c + 1]) - delta));
         }
       }
-      uint8_t* sds = smem + S::OFF_T0 + buf * S::T_BYTES + r_in * 128;
-#pragma unroll
-      for (int ch = 0; ch < AB_PC / 8; ++ch)
-        *reinterpret_cast<uint4*>(sds + (((part * (AB_PC / 8) + ch) ^ sw) << 4)) =
-            make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+      tmem_st8(t_lane + TM_S + buf * 128 + part * AB_PC, pk);   // dS(j) over the S(j) columns this thread has consumed
       TRACE(0, j, 3);
-      fence_proxy_async();
+      tmem_st_wait();
       TRACE(0, j, 4);
       tc_fence_before();
       __syncwarp();
@@ -338,6 +367,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   constexpr int TM_S = 0;             // S^T[buf] at buf*128, dP^T[buf] at buf*128 + 64
   constexpr int TM_DV = 256;          // D columns
   constexpr int TM_DK = 256 + D;      // D columns (D <= 128)
+  // K / V rows as TMEM-resident A operands of S^T and dP^T (fits only at D = 64). Implemented and parity-tested, but measured
+  // +2.5 % on the whole backward (the A reads compete with the math warps' tcgen05.ld / st for TMEM bandwidth): left off.
+  constexpr bool kKT = false;
+  constexpr int TM_K = 256 + 2 * D;   // D/2 columns
+  constexpr int TM_V = 256 + 2 * D + D / 2;
   constexpr uint32_t IDESC_S = make_idesc_bf16(AB_BM, AB_BN, 0, 0);
   constexpr uint32_t IDESC_DKV = make_idesc_bf16(AB_BM, D, 0, 1);
 
@@ -362,7 +396,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
 
   if (warp == AB_W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmdO); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
-    mbar_init(big_full, 1);
+    mbar_init(big_full, kKT ? AB_MATH / 32 : 1);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&sml_full[i], 1); mbar_init(&sml_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&t_ready[i], AB_MATH / 32); }
     mbar_init(done, 1);
@@ -378,11 +412,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     if (lane == 0) {
       const int qc = head * p.q_head_stride, dc = head * p.do_head_stride;
       const int kc = head * p.k_head_stride, vc = head * p.v_head_stride;
-      mbar_expect_tx(big_full, 2 * S::BIG_BYTES);
+      if constexpr (!kKT) {
+        mbar_expect_tx(big_full, 2 * S::BIG_BYTES);
 #pragma unroll
-      for (int h = 0; h < D / 64; ++h) {
-        tma_load_3d(smem + S::OFF_BIG0 + h * (AB_BM * 128), &tmK, big_full, kc + h * 64, kv0, b);
-        tma_load_3d(smem + S::OFF_BIG1 + h * (AB_BM * 128), &tmV, big_full, vc + h * 64, kv0, b);
+        for (int h = 0; h < D / 64; ++h) {
+          tma_load_3d(smem + S::OFF_BIG0 + h * (AB_BM * 128), &tmK, big_full, kc + h * 64, kv0, b);
+          tma_load_3d(smem + S::OFF_BIG1 + h * (AB_BM * 128), &tmV, big_full, vc + h * 64, kv0, b);
+        }
       }
       int st = 0; uint32_t ph = 0;
       for (int i = 0; i < n_steps; ++i) {
@@ -405,26 +441,27 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     const uint64_t dsc_do = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML1), 0, 1024);
     const uint64_t dsc_qmn = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML0), AB_BN * 128, 1024);  // MN-major view (dK)
     const uint64_t dsc_domn = make_smem_desc_sw128(smem_u32(smem + S::OFF_SML1), AB_BN * 128, 1024); // MN-major view (dV)
-    const uint64_t dsc_pt = make_smem_desc_sw128(smem_u32(smem + S::OFF_T0), 0, 1024);
-    const uint64_t dsc_dst = make_smem_desc_sw128(smem_u32(smem + S::OFF_T1), 0, 1024);
     auto issue_st_dpt = [&](int buf, int st) {
       if (elect_one()) {
         const uint64_t sto = uint64_t(st) * (S::SML_BYTES >> 4);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t oa = ((kk / 4) * (AB_BM * 128) + (kk % 4) * 32) >> 4, ob = ((kk / 4) * (AB_BN * 128) + (kk % 4) * 32) >> 4;
-          umma_bf16(tmem_base + TM_S + buf * 128, dsc_k + oa, dsc_q + sto + ob, IDESC_S, kk != 0);
+          if constexpr (kKT) umma_bf16_ts(tmem_base + TM_S + buf * 128, tmem_base + TM_K + kk * 8, dsc_q + sto + ob, IDESC_S, kk != 0);
+          else umma_bf16(tmem_base + TM_S + buf * 128, dsc_k + oa, dsc_q + sto + ob, IDESC_S, kk != 0);
         }
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk) {
           const uint32_t oa = ((kk / 4) * (AB_BM * 128) + (kk % 4) * 32) >> 4, ob = ((kk / 4) * (AB_BN * 128) + (kk % 4) * 32) >> 4;
-          umma_bf16(tmem_base + TM_S + buf * 128 + 64, dsc_v + oa, dsc_do + sto + ob, IDESC_S, kk != 0);
+          if constexpr (kKT) umma_bf16_ts(tmem_base + TM_S + buf * 128 + 64, tmem_base + TM_V + kk * 8, dsc_do + sto + ob, IDESC_S, kk != 0);
+          else umma_bf16(tmem_base + TM_S + buf * 128 + 64, dsc_v + oa, dsc_do + sto + ob, IDESC_S, kk != 0);
         }
         umma_commit(&s_full[buf]);
       }
       __syncwarp();
     };
     mbar_wait(big_full, 0);
+    tc_fence_after();
     if (n_steps > 0) {
       mbar_wait(&sml_full[0], 0);
       tc_fence_after();
@@ -442,15 +479,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
       mbar_wait(&t_ready[i & 1], (i >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t tb = uint64_t(i & 1) * (S::T_BYTES >> 4), sto = uint64_t(st) * (S::SML_BYTES >> 4);
+        // P^T(i) / dS^T(i) are read from TENSOR MEMORY: query slice kk sits where column part kk read its S^T / dP^T values
+        const uint64_t sto = uint64_t(st) * (S::SML_BYTES >> 4);
+        const uint32_t ta = tmem_base + TM_S + (i & 1) * 128;
 #pragma unroll
         for (int kk = 0; kk < AB_BN / 16; ++kk)
-          umma_bf16(tmem_base + TM_DV, dsc_pt + tb + ((kk * 32) >> 4), dsc_domn + sto + ((kk * 2048) >> 4), IDESC_DKV,
-                    (i | kk) != 0);
+          umma_bf16_ts(tmem_base + TM_DV, ta + 16 * kk, dsc_domn + sto + ((kk * 2048) >> 4), IDESC_DKV, (i | kk) != 0);
 #pragma unroll
         for (int kk = 0; kk < AB_BN / 16; ++kk)
-          umma_bf16(tmem_base + TM_DK, dsc_dst + tb + ((kk * 32) >> 4), dsc_qmn + sto + ((kk * 2048) >> 4), IDESC_DKV,
-                    (i | kk) != 0);
+          umma_bf16_ts(tmem_base + TM_DK, ta + 64 + 16 * kk, dsc_qmn + sto + ((kk * 2048) >> 4), IDESC_DKV, (i | kk) != 0);
         umma_commit(&sml_empty[st]);
       }
       __syncwarp();
@@ -467,9 +504,28 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     bool row_ok = kv_row < p.seq_kv;
     const bool store_ok = row_ok;
     if (row_ok && p.kv_mask) row_ok = p.kv_mask[int64_t(b) * p.seq_kv + kv_row] != 0;
-    const int sw = r_in & 7;
     const int64_t stat_base = (int64_t(b) * p.nheads + head) * p.seq_q;
     const bool vec_stats = (p.seq_q % 4) == 0;   // 16-byte aligned rows of lse / delta
+    if constexpr (kKT) {  // park this thread's quarter of its K and V rows in TMEM (A operands of S^T and dP^T)
+      constexpr int W = D / 2 / AB_PARTS;
+      uint32_t wk[W], wv[W];
+      const uint4* gk = reinterpret_cast<const uint4*>(p.k + (int64_t(b) * p.seq_kv + kv_row) * p.k_row_stride +
+                                                       int64_t(head) * p.k_head_stride + part * (2 * W));
+      const uint4* gv = reinterpret_cast<const uint4*>(p.v + (int64_t(b) * p.seq_kv + kv_row) * p.v_row_stride +
+                                                       int64_t(head) * p.v_head_stride + part * (2 * W));
+#pragma unroll
+      for (int i = 0; i < W / 4; ++i) {
+        const uint4 a = store_ok ? gk[i] : make_uint4(0, 0, 0, 0), c = store_ok ? gv[i] : make_uint4(0, 0, 0, 0);
+        wk[4 * i] = a.x; wk[4 * i + 1] = a.y; wk[4 * i + 2] = a.z; wk[4 * i + 3] = a.w;
+        wv[4 * i] = c.x; wv[4 * i + 1] = c.y; wv[4 * i + 2] = c.z; wv[4 * i + 3] = c.w;
+      }
+      if constexpr (W == 8) { tmem_st8(t_lane + TM_K + part * W, wk); tmem_st8(t_lane + TM_V + part * W, wv); }
+      else { tmem_st16(t_lane + TM_K + part * W, wk); tmem_st16(t_lane + TM_V + part * W, wv); }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(big_full);
+    }
     for (int i = 0; i < n_steps; ++i) {
       const int buf = i & 1;
       const int qt0 = (i_start + i) * AB_BN;
@@ -515,16 +571,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         pp[c >> 1] = pack_bf16x2(pv[0], pv[1]);
         pd[c >> 1] = pack_bf16x2(dv[0], dv[1]);
       }
-      uint8_t* spt = smem + S::OFF_T0 + buf * S::T_BYTES + r_in * 128;
-      uint8_t* sdst = smem + S::OFF_T1 + buf * S::T_BYTES + r_in * 128;
-#pragma unroll
-      for (int ch = 0; ch < AB_PC / 8; ++ch) {
-        *reinterpret_cast<uint4*>(spt + (((part * (AB_PC / 8) + ch) ^ sw) << 4)) =
-            make_uint4(pp[ch * 4], pp[ch * 4 + 1], pp[ch * 4 + 2], pp[ch * 4 + 3]);
-        *reinterpret_cast<uint4*>(sdst + (((part * (AB_PC / 8) + ch) ^ sw) << 4)) =
-            make_uint4(pd[ch * 4], pd[ch * 4 + 1], pd[ch * 4 + 2], pd[ch * 4 + 3]);
-      }
-      fence_proxy_async();
+      // P^T(i) / dS^T(i) go back to TMEM over the S^T / dP^T columns this thread has just consumed (A operands of dV / dK)
+      tmem_st8(t_lane + TM_S + buf * 128 + part * AB_PC, pp);
+      tmem_st8(t_lane + TM_S + buf * 128 + 64 + part * AB_PC, pd);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_ready[buf]);
@@ -652,6 +702,8 @@ extern "C" int fsb_sdpa_bwd(const void* q, const void* k, const void* v, const v
               "sdpa_bwd: strides must be multiples of 8 elements");
   AttBwdParams p;
   p.lse = lse; p.delta = delta; p.kv_mask = kv_mask;
+  p.q = (const __nv_bfloat16*)q; p.dout = (const __nv_bfloat16*)dout; p.q_row_stride = q_row_stride; p.do_row_stride = do_row_stride;
+  p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v; p.k_row_stride = k_row_stride; p.v_row_stride = v_row_stride;
   p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
   p.dq_row_stride = dq_row_stride; p.dk_row_stride = dk_row_stride; p.dv_row_stride = dv_row_stride;
   p.dq_head_stride = dq_head_stride; p.dk_head_stride = dk_head_stride; p.dv_head_stride = dv_head_stride;
