@@ -370,8 +370,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   // K / V rows as TMEM-resident A operands of S^T and dP^T (fits only at D = 64). Implemented and parity-tested, but measured
   // +2.5 % on the whole backward (the A reads compete with the math warps' tcgen05.ld / st for TMEM bandwidth): left off.
   constexpr bool kKT = false;
-  constexpr int TM_K = 256 + 2 * D;   // D/2 columns
-  constexpr int TM_V = 256 + 2 * D + D / 2;
+  [[maybe_unused]] constexpr int TM_K = 256 + 2 * D;   // D/2 columns
+  [[maybe_unused]] constexpr int TM_V = 256 + 2 * D + D / 2;
   constexpr uint32_t IDESC_S = make_idesc_bf16(AB_BM, AB_BN, 0, 0);
   constexpr uint32_t IDESC_DKV = make_idesc_bf16(AB_BM, D, 0, 1);
 
