@@ -10,6 +10,8 @@
 // Weight gradients: every thread accumulates fp32 partials over its rows; the CTA combines its RPC row slots through
 // shared memory in a fixed order and writes partial[cta, cols]; a second kernel reduces the partials column-wise
 // (deterministic, no atomics).
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -236,8 +238,18 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ p
   const int col = blockIdx.x * 32 + (threadIdx.x & 31);
   const int rl = threadIdx.x >> 5;
   float s = 0.f;
-  if (col < width)
-    for (int r = rl; r < nparts; r += 8) s += partial[size_t(r) * width + col];
+  if (col < width) {
+    // fixed summation order (deterministic), eight independent loads in flight per thread: the chain of dependent
+    // L2 round trips, not bandwidth, is what this stage costs
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int r = rl;
+    for (; r + 56 < nparts; r += 64) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += partial[size_t(r + 8 * u) * width + col];
+    }
+    for (int u = 0; r < nparts; r += 8, ++u) a[u] += partial[size_t(r) * width + col];
+    s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  }
   sm[rl][threadIdx.x & 31] = s;
   __syncthreads();
   if (rl == 0 && col < width) {
@@ -263,10 +275,20 @@ static void norm_shape(int64_t cols, int& tpr, int& vpt) {
   while (tpr < 256 && (nvec + tpr - 1) / tpr > 4) tpr *= 2;
   vpt = (nvec + tpr - 1) / tpr;
 }
+// backward: the thread also carries fp32 weight-gradient partials for every column it owns, so at most 3 vectors per thread
+// (with 4: 162 registers, ONE resident CTA per SM, 1.5 TB/s on 16384 x 2048 — rows in flight, not bandwidth, bound it;
+// with 2-3: 80-123 registers, 2-3 CTAs per SM, 2.5 TB/s)
+static void norm_shape_bwd(int64_t cols, int& tpr, int& vpt) {
+  const int nvec = int(cols / 8);
+  tpr = 32;
+  while (tpr < 256 && (nvec + tpr - 1) / tpr > 3) tpr *= 2;
+  vpt = (nvec + tpr - 1) / tpr;
+}
 static int norm_grid(int64_t rows, int tpr) {
   const int rpc = NORM_THREADS / tpr;
   const int64_t groups = (rows + rpc - 1) / rpc;
-  const int64_t cap = int64_t(4) * num_sms();
+  static const int mult = [] { const char* e = getenv("FSB_NORM_GRID_MULT"); return e ? atoi(e) : 4; }();   // CTAs per SM (tuning knob)
+  const int64_t cap = int64_t(mult) * num_sms();
   return int(groups < cap ? groups : cap);
 }
 
@@ -274,9 +296,12 @@ static int norm_grid(int64_t rows, int tpr) {
   switch (tpr) {                                                                                               \
     case 32:  switch (vpt) { case 1: KERNEL_LAUNCH(32, 1); break; case 2: KERNEL_LAUNCH(32, 2); break;         \
                              case 3: KERNEL_LAUNCH(32, 3); break; default: KERNEL_LAUNCH(32, 4); break; } break; \
-    case 64:  switch (vpt) { case 3: KERNEL_LAUNCH(64, 3); break; default: KERNEL_LAUNCH(64, 4); break; } break; \
-    case 128: switch (vpt) { case 3: KERNEL_LAUNCH(128, 3); break; default: KERNEL_LAUNCH(128, 4); break; } break; \
-    default:  switch (vpt) { case 3: KERNEL_LAUNCH(256, 3); break; case 4: KERNEL_LAUNCH(256, 4); break;        \
+    case 64:  switch (vpt) { case 1: KERNEL_LAUNCH(64, 1); break; case 2: KERNEL_LAUNCH(64, 2); break;         \
+                             case 3: KERNEL_LAUNCH(64, 3); break; default: KERNEL_LAUNCH(64, 4); break; } break; \
+    case 128: switch (vpt) { case 1: KERNEL_LAUNCH(128, 1); break; case 2: KERNEL_LAUNCH(128, 2); break;       \
+                             case 3: KERNEL_LAUNCH(128, 3); break; default: KERNEL_LAUNCH(128, 4); break; } break; \
+    default:  switch (vpt) { case 1: KERNEL_LAUNCH(256, 1); break; case 2: KERNEL_LAUNCH(256, 2); break;        \
+                             case 3: KERNEL_LAUNCH(256, 3); break; case 4: KERNEL_LAUNCH(256, 4); break;        \
                              case 5: KERNEL_LAUNCH(256, 5); break; case 6: KERNEL_LAUNCH(256, 6); break;        \
                              case 7: KERNEL_LAUNCH(256, 7); break; default: KERNEL_LAUNCH(256, 8); break; } break; \
   }
@@ -326,7 +351,7 @@ static int norm_bwd(const void* dy, const void* x, const void* gamma, const floa
   FSB_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(gamma) && aligned16(dres) && aligned16(dx),
               "norm_bwd: pointers must be 16-byte aligned");
   int tpr, vpt;
-  norm_shape(cols, tpr, vpt);
+  norm_shape_bwd(cols, tpr, vpt);
   const int grid = norm_grid(rows, tpr);
   const int width = int(cols) * (kLayer ? 2 : 1);
   const size_t need = size_t(grid) * width * sizeof(float);
@@ -359,7 +384,7 @@ using namespace fsb;
 
 extern "C" size_t fsb_norm_bwd_workspace_bytes(int64_t rows, int64_t cols, int is_layernorm) {
   int tpr, vpt;
-  norm_shape(cols, tpr, vpt);
+  norm_shape_bwd(cols, tpr, vpt);
   return size_t(norm_grid(rows, tpr)) * size_t(cols) * (is_layernorm ? 2 : 1) * sizeof(float);
 }
 extern "C" int fsb_rmsnorm_fwd(const void* x, const void* residual, const void* scale, void* y, void* sum_out,
