@@ -150,7 +150,13 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_bwd_kernel(
     const float mean = (kLayer && rv) ? stats[2 * row] : 0.f;
     const float rstd = rv ? (kLayer ? stats[2 * row + 1] : stats[row]) : 0.f;
     float xh[VPT][8], g[VPT][8];
+    uint4 rq[VPT];   // residual-branch gradient, fetched WITH x / dy (one memory round trip per row instead of two)
     float s_g = 0.f, s_gx = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      const int c = lir + i * TPR;
+      rq[i] = (dres != nullptr && rv && c < nvec) ? dres[base + c] : make_uint4(0, 0, 0, 0);
+    }
 #pragma unroll
     for (int i = 0; i < VPT; ++i) {
       const int c = lir + i * TPR;
@@ -183,9 +189,9 @@ __global__ void __launch_bounds__(NORM_THREADS) norm_bwd_kernel(
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - m_g - xh[i][j] * m_gx);
-        if (dres != nullptr) {
+        {
           float r[8];
-          unpack8(dres[base + c], r);
+          unpack8(rq[i], r);   // zeros when there is no residual branch
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += r[j];
         }
