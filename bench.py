@@ -81,12 +81,15 @@ def flops_per_token(w):
 # (profiles/r01_ncu_gemm_v3.summary.txt; dram__bytes_read.sum + dram__bytes_write.sum, one launch), next to its algorithmic
 # bytes (A + B read once, D written once). bench.py cannot run ncu itself, so these are constants tied to that capture.
 NCU_TRAFFIC = {
-    "gpt2": {"launch": "fsb::gemm_bf16_kernel NN 32768x3072x768 (c_fc forward)", "traffic": 55.156224e6 + 144.0e6,
-             "algorithmic": (32768 * 768 + 768 * 3072 + 32768 * 3072) * 2.0,
-             "source": "profiles/r01_ncu_gemm_v3.summary.txt"},
-    "llama": {"launch": "fsb::gemm_bf16_kernel NT 8192x15360x5120 (QKV forward)", "traffic": 584.21e6 + 236.86e6,
-              "algorithmic": (8192 * 5120 + 15360 * 5120 + 8192 * 15360) * 2.0,
-              "source": "profiles/r01_ncu_gemm_v3.summary.txt (after the rasterisation change; 1379 MB + 239 MB before)"},
+    "gpt2": {"launch": "fsb::gemm_bf16_kernel<NN,256,pair> 32768x3072x768 (c_fc forward)", "traffic": 60.866304e6 + 146.682112e6,
+             "algorithmic": (32768 * 768 + 768 * 3072 + 32768 * 3072) * 2.0, "tensor_pipe_active_pct": 78.4,
+             "source": "profiles/r01_ncu_gemm_final.summary.txt"},
+    "bert": {"launch": "fsb::gemm_bf16_kernel<NN,256,pair> 32768x3072x768 (same MLP shape family)", "traffic": 60.866304e6 + 146.682112e6,
+             "algorithmic": (32768 * 768 + 768 * 3072 + 32768 * 3072) * 2.0, "tensor_pipe_active_pct": 78.4,
+             "source": "profiles/r01_ncu_gemm_final.summary.txt"},
+    "llama": {"launch": "fsb::gemm_bf16_kernel<NT,256,pair> 8192x15360x5120 (QKV forward)", "traffic": 711.888384e6 + 240.509952e6,
+              "algorithmic": (8192 * 5120 + 15360 * 5120 + 8192 * 15360) * 2.0, "tensor_pipe_active_pct": 98.4,
+              "source": "profiles/r01_ncu_gemm_final.summary.txt"},
 }
 
 
