@@ -56,6 +56,11 @@ int fsb_num_sms(void);               /* SM count of the current device (148 on B
  * Requirements: pointers 16-byte aligned; lda/ldb/ldd multiples of 8 elements.
  * aux (bf16, may be NULL): receives acc + bias BEFORE the activation (saved for the activation's backward).
  * `batch` > 1 runs independent GEMMs with element strides stride_a/b/d between them (use 1 and 0 otherwise).
+ * Kernel selection is internal: CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles) when the output has at least one such tile
+ * per SM pair, single-CTA 128 x 256 / 128 x 128 tiles otherwise. FSB_GEMM_TN calls whose output has few tiles and K >= 4096
+ * (weight gradients of small models) split K: the chunks are accumulated in fp32 in a per-device scratch the library grows on
+ * first use and reduced in a fixed order (results are deterministic); such calls must not run concurrently on several streams.
+ * FSB_EPI_GELU_ERF evaluates erf through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, below the bf16 rounding of the output).
  */
 typedef enum { FSB_GEMM_NT = 0, FSB_GEMM_NN = 1, FSB_GEMM_TN = 2 } fsb_gemm_layout;
 typedef enum {
