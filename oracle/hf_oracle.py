@@ -114,3 +114,58 @@ def train_gpt2(model, batches, steps, lr=1e-3, weight_decay=0.1, warmup=2):
         opt.step()
         losses.append(float(loss.detach()))
     return losses
+
+
+# ------------------------------------------------------------------------------------------------ C5: mT5 (round-2 row)
+# examples/pretrain_t5/pretrain_t5.py:57-59 builds transformers.MT5ForConditionalGeneration(MT5Config); training_step
+# (:81-87) is `self.model(input_ids=..., labels=...)` — HF shifts the labels right itself, T5LayerNorm is an RMSNorm without
+# mean subtraction, attention is UNSCALED with an additive relative-position bias shared by all layers of a stack, the FFN is
+# gated-GELU (wi_0, wi_1, wo), nothing has a bias, lm_head is untied for mT5 (tie_word_embeddings=False).
+MT5_SMALL = dict(vocab_size=512, d_model=256, d_kv=64, d_ff=512, num_layers=2, num_decoder_layers=2, num_heads=4,
+                 relative_attention_num_buckets=32, relative_attention_max_distance=128)
+
+
+def build_mt5(cfg, seed=0, bf16_exact=True):
+    from transformers import MT5Config, MT5ForConditionalGeneration
+    torch.manual_seed(seed)
+    config = MT5Config(dropout_rate=0.0, feed_forward_proj="gated-gelu", tie_word_embeddings=False,
+                       attn_implementation="eager", decoder_start_token_id=0, pad_token_id=0, **cfg)
+    model = MT5ForConditionalGeneration(config)
+    model.train()
+    return _bf16_exact_(model) if bf16_exact else model
+
+
+def make_t5_batch(V, B, S_enc, S_dec, seed=1234, pad_tail=0):
+    """Synthetic span-corruption-shaped batch: encoder ids + attention mask, decoder labels with -100 on the padded tail."""
+    rng = np.random.RandomState(seed)
+    ids = rng.randint(2, V, size=(B, S_enc)).astype(np.int64)
+    am = np.ones((B, S_enc), dtype=np.int64)
+    if pad_tail:
+        ids[-1, -pad_tail:] = 0
+        am[-1, -pad_tail:] = 0
+    labels = rng.randint(2, V, size=(B, S_dec)).astype(np.int64)
+    labels[:, -3:] = -100
+    return {"input_ids": torch.from_numpy(ids), "attention_mask": torch.from_numpy(am), "labels": torch.from_numpy(labels)}
+
+
+def t5_relative_position_bucket(rel, bidirectional, num_buckets=32, max_distance=128):
+    """Restatement (numpy, integer in / integer out) of transformers' T5Attention._relative_position_bucket
+    (models/t5/modeling_t5.py, static method): rel = key_pos - query_pos. This is the function the CUDA attention kernels
+    will evaluate per (q, k) pair to index the [num_buckets, heads] bias table; tests pin it to HF bit-exactly."""
+    rel = np.asarray(rel, dtype=np.int64)
+    out = np.zeros_like(rel)
+    nb = num_buckets
+    if bidirectional:
+        nb //= 2
+        out += (rel > 0).astype(np.int64) * nb
+        rel = np.abs(rel)
+    else:
+        rel = -np.minimum(rel, 0)
+    max_exact = nb // 2
+    is_small = rel < max_exact
+    # float32 arithmetic exactly as torch does it (log in fp32, truncation towards zero)
+    relf = np.maximum(rel, 1).astype(np.float32)
+    large = max_exact + (np.log(relf / np.float32(max_exact)) / np.float32(np.log(max_distance / max_exact))
+                         * np.float32(nb - max_exact)).astype(np.int64)
+    large = np.minimum(large, nb - 1)
+    return out + np.where(is_small, rel, large)

@@ -40,6 +40,25 @@ def main():
     np.savez_compressed(os.path.join(OUT, "bert_small.npz"), bert_loss=np.array(lb), megatron_loss=np.array(lm),
                         transformers_version=np.array(transformers.__version__))
     print("bert_small: bert", lb, "megatron", lm)
+    # C5 mT5 (oracle row for round 2): loss, logits slice, gradient norms, and the relative-position bucket tables
+    Vt = H.MT5_SMALL["vocab_size"]
+    m5 = H.build_mt5(H.MT5_SMALL)
+    tb = H.make_t5_batch(Vt, 2, 96, 48, seed=7, pad_tail=13)
+    o5 = m5(**tb)
+    o5.loss.backward()
+    rec5 = {"loss": np.array(o5.loss.item()), "logits_slice": o5.logits.detach()[:, :, :64].numpy(),
+            "transformers_version": np.array(transformers.__version__)}
+    for n, p in m5.named_parameters():
+        if p.grad is not None:
+            rec5["gradnorm/" + n] = np.array(p.grad.norm().item())
+    from transformers.models.t5.modeling_t5 import T5Attention
+    rel = torch.arange(-300, 301)
+    rec5["bucket_bidirectional"] = T5Attention._relative_position_bucket(rel, bidirectional=True, num_buckets=32,
+                                                                         max_distance=128).numpy()
+    rec5["bucket_causal"] = T5Attention._relative_position_bucket(rel, bidirectional=False, num_buckets=32,
+                                                                  max_distance=128).numpy()
+    np.savez_compressed(os.path.join(OUT, "mt5_small.npz"), **rec5)
+    print("mt5_small: loss", o5.loss.item())
 
 
 if __name__ == "__main__":
