@@ -5,7 +5,7 @@
 // without the three repacking copies of q/k/v (transformer.py:419-429): Q, K, V are read straight out of the packed
 // QKV projection output through TMA tensor maps (any row/head stride), O is written in [token, head*dim] layout.
 //
-// CTA = one (batch, head, pair of 128-row Q tiles), 10 warps:
+// CTA = one (batch, head, pair of 128-row Q tiles), 12 warps (warps 10-11 only donate registers through setmaxnreg):
 //   warps 0-3 / 4-7 : softmax group of Q tile 0 / 1. TMEM lane == query row == thread: a thread owns the 64 scores of its
 //                     row for the step, so row max / row sum need no cross-thread exchange; S(j+1) is prefetched from
 //                     TMEM into a second register set while the exponentials of step j run.
