@@ -235,6 +235,62 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
     if (c < cols) partial[int64_t(blockIdx.y) * cols + c] = t;
   }
 }
+// dx = dy * act'(x) AND partial column sums of dx in the same pass (the bias gradient of the linear layer that produced x).
+// A CTA owns 256 columns x a strip of rows: every warp streams whole 512-byte row segments (three streams: x, dy, dx), two rows
+// in flight per thread; the 8 row lanes are combined through shared memory and written as partial[strip, cols].
+template <int ACT>
+__global__ void __launch_bounds__(256) act_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                             __nv_bfloat16* __restrict__ dx, float* __restrict__ partial,
+                                                             int64_t rows, int cols, int rows_per_strip) {
+  __shared__ float sm[8][256 + 4];
+  const int cl = threadIdx.x & 31;
+  const int rl = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + cl * 8;
+  const int64_t r0 = int64_t(blockIdx.y) * rows_per_strip;
+  const int64_t r1 = min(rows, r0 + rows_per_strip);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < cols) {
+    for (int64_t r = r0 + rl; r < r1; r += 16) {
+      const bool two = r + 8 < r1;
+      const uint4 xa = *reinterpret_cast<const uint4*>(x + r * cols + col);
+      const uint4 da = *reinterpret_cast<const uint4*>(dy + r * cols + col);
+      uint4 xb = make_uint4(0, 0, 0, 0), db = make_uint4(0, 0, 0, 0);
+      if (two) {
+        xb = *reinterpret_cast<const uint4*>(x + (r + 8) * cols + col);
+        db = *reinterpret_cast<const uint4*>(dy + (r + 8) * cols + col);
+      }
+      float a[8], d[8], o[8], f[8];
+      unpack8(xa, a); unpack8(da, d);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = d[j] * dact_f<ACT>(a[j]);
+      uint4 q = pack8(o);
+      *reinterpret_cast<uint4*>(dx + r * cols + col) = q;
+      unpack8(q, f);   // sum what was stored (bf16-rounded): exactly what a separate colsum over dx would add up
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      if (two) {
+        unpack8(xb, a); unpack8(db, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = d[j] * dact_f<ACT>(a[j]);
+        q = pack8(o);
+        *reinterpret_cast<uint4*>(dx + (r + 8) * cols + col) = q;
+        unpack8(q, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[rl][cl * 8 + j] = acc[j];
+  __syncthreads();
+  {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x];
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < cols) partial[int64_t(blockIdx.y) * cols + c] = t;
+  }
+}
 __global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partial, void* __restrict__ out,
                                                             int nparts, int cols, int out_f32, int accumulate) {
   const int c = blockIdx.x * 256 + threadIdx.x;
@@ -411,6 +467,41 @@ extern "C" int fsb_colsum(const void* x, int64_t rows, int64_t cols, int64_t ld,
   FSB_CUDA_LAUNCH_CHECK();
   colsum_finish_kernel<<<unsigned((cols + 255) / 256), 256, 0, (cudaStream_t)st>>>((const float*)workspace, out, ns,
                                                                                   int(cols), out_dtype == FSB_F32, accumulate);
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+static void act_bwd_bias_plan(int64_t rows, int64_t cols, int& nstrips, int& rows_per_strip) {
+  const int col_tiles = int((cols + 255) / 256);
+  int64_t want = (int64_t(8) * num_sms() + col_tiles - 1) / col_tiles;
+  const int64_t max_strips = (rows + 15) / 16;
+  if (want > max_strips) want = max_strips;
+  if (want < 1) want = 1;
+  if (want > 2048) want = 2048;
+  rows_per_strip = int(((rows + want - 1) / want + 15) / 16 * 16);
+  nstrips = int((rows + rows_per_strip - 1) / rows_per_strip);
+}
+extern "C" size_t fsb_act_bwd_bias_workspace_bytes(int64_t rows, int64_t cols) {
+  int ns, rps;
+  act_bwd_bias_plan(rows, cols, ns, rps);
+  return size_t(ns) * size_t(cols) * sizeof(float);
+}
+extern "C" int fsb_act_bwd_bias(int act, const void* dy, const void* x, void* dx, int64_t rows, int64_t cols, void* dbias,
+                                int dbias_dtype, int accumulate, void* workspace, size_t workspace_bytes, fsb_stream_t st) {
+  FSB_REQUIRE(dy && x && dx && dbias && workspace && rows > 0 && cols > 0 && cols % 8 == 0 && aligned16(dy) && aligned16(x) &&
+                  aligned16(dx),
+              "act_bwd_bias: bad args (cols multiple of 8; 16-byte aligned, contiguous rows)");
+  FSB_REQUIRE(act >= 1 && act <= 3, "act_bwd_bias: act %d unsupported (1 tanh-GeLU, 2 erf-GeLU, 3 tanh)", act);
+  int ns, rps;
+  act_bwd_bias_plan(rows, cols, ns, rps);
+  FSB_REQUIRE(workspace_bytes >= size_t(ns) * cols * sizeof(float), "act_bwd_bias: workspace too small");
+  dim3 grid(unsigned((cols + 255) / 256), unsigned(ns));
+  const __nv_bfloat16 *pdy = (const __nv_bfloat16*)dy, *px = (const __nv_bfloat16*)x;
+  if (act == 1) act_bwd_colsum_kernel<1><<<grid, 256, 0, (cudaStream_t)st>>>(pdy, px, (__nv_bfloat16*)dx, (float*)workspace, rows, int(cols), rps);
+  else if (act == 2) act_bwd_colsum_kernel<2><<<grid, 256, 0, (cudaStream_t)st>>>(pdy, px, (__nv_bfloat16*)dx, (float*)workspace, rows, int(cols), rps);
+  else act_bwd_colsum_kernel<3><<<grid, 256, 0, (cudaStream_t)st>>>(pdy, px, (__nv_bfloat16*)dx, (float*)workspace, rows, int(cols), rps);
+  FSB_CUDA_LAUNCH_CHECK();
+  colsum_finish_kernel<<<unsigned((cols + 255) / 256), 256, 0, (cudaStream_t)st>>>((const float*)workspace, dbias, ns,
+                                                                                  int(cols), dbias_dtype == FSB_F32, accumulate);
   FSB_CUDA_LAUNCH_CHECK();
   return FSB_OK;
 }

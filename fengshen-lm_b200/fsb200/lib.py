@@ -45,6 +45,9 @@ SIGNATURES = {
                             c_i64, c_i64, c_i64, c_void_p]),
     "fsb_act_fwd": (c_int, [c_int, c_void_p, c_void_p, c_i64, c_void_p]),
     "fsb_act_bwd": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "fsb_act_bwd_bias_workspace_bytes": (c_size, [c_i64, c_i64]),
+    "fsb_act_bwd_bias": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p, c_int, c_int, c_void_p, c_size,
+                                 c_void_p]),
     "fsb_add": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     "fsb_accumulate": (c_int, [c_void_p, c_void_p, c_i64, c_f32, c_int, c_void_p]),
     "fsb_scale_inplace": (c_int, [c_void_p, c_i64, c_void_p, c_void_p]),
@@ -109,7 +112,7 @@ def check(rc, what):
 kernel_launches = 0  # number of __global__ launches issued by the library on behalf of this process
 # kernels launched per successful entry-point call (everything not listed launches exactly one)
 _KERNELS_PER_CALL = {"fsb_rmsnorm_bwd": 2, "fsb_layernorm_bwd": 2, "fsb_softmax_xent_fwd_bwd": 3, "fsb_sdpa_bwd": 3,
-                     "fsb_sumsq": 2, "fsb_colsum": 2}
+                     "fsb_sumsq": 2, "fsb_colsum": 2, "fsb_act_bwd_bias": 2}
 
 
 call_profiler = None  # optional: object with .add(name, ev0, ev1, work); set by bench.py --breakdown (CUDA events per call)

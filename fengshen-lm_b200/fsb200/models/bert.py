@@ -333,9 +333,8 @@ class _BertFamily(nn.Module):
             df = ops.gemm(L.GEMM_NN, dm, w2.data)
             ops.gemm(L.GEMM_TN, dm, f, out=w2.main_grad, accumulate=acc)
             ops.colsum(dm, b2.main_grad, accumulate=acc)
-            dprea = ops.act_bwd(self.act, df, prea)
+            dprea = ops.act_bwd_bias(self.act, df, prea, b1.main_grad, accumulate=acc)   # dGELU + intermediate.dense bias grad
             ops.gemm(L.GEMM_TN, dprea, h2, out=w1.main_grad, accumulate=acc)
-            ops.colsum(dprea, b1.main_grad, accumulate=acc)
             if pre:
                 dh2 = ops.gemm(L.GEMM_NN, dprea, w1.data)
                 lw, lb = P(p + "ln.weight"), P(p + "ln.bias")

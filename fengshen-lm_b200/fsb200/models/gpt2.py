@@ -197,11 +197,10 @@ class GPT2LMHeadModel(nn.Module):
             df = ops.gemm(L.GEMM_NT, dx, w.weight.data)
             ops.gemm(L.GEMM_TN, f, dx, out=w.weight.main_grad, accumulate=acc)
             ops.colsum(dx, w.bias.main_grad, accumulate=acc)
-            dpre = ops.act_bwd(L.ACT_GELU_TANH, df, pre)
             w = blk.mlp.c_fc
+            dpre = ops.act_bwd_bias(L.ACT_GELU_TANH, df, pre, w.bias.main_grad, accumulate=acc)   # dGELU + c_fc bias grad
             dh2 = ops.gemm(L.GEMM_NT, dpre, w.weight.data)
             ops.gemm(L.GEMM_TN, h2, dpre, out=w.weight.main_grad, accumulate=acc)
-            ops.colsum(dpre, w.bias.main_grad, accumulate=acc)
             dx1 = ops.layernorm_bwd(dh2, x1, blk.ln_2.weight.data, st2, blk.ln_2.weight.main_grad,
                                     blk.ln_2.bias.main_grad, accumulate=acc, dres=dx)
             w = blk.attn.c_proj

@@ -199,6 +199,20 @@ def act_bwd(act, dy, x):
     return dx
 
 
+def act_bwd_bias(act, dy, x, dbias, accumulate=False):
+    """dx = dy * act'(x) and dbias[c] (+)= sum_r dx[r, c] in one pass (x, dy contiguous [rows, cols])."""
+    _chk(x, _bf16, "x"); _chk(dy, _bf16, "dy")
+    if not (x.is_contiguous() and dy.is_contiguous()) or x.dim() != 2 or dy.shape != x.shape:
+        raise RuntimeError("fsb200 act_bwd_bias: x and dy must be contiguous [rows, cols] of the same shape")
+    rows, cols = x.shape
+    dx = torch.empty_like(x)
+    nbytes = L.load().fsb_act_bwd_bias_workspace_bytes(rows, cols)
+    ws = workspace(nbytes, x.device, "act_bwd_bias")
+    L.call("fsb_act_bwd_bias", act, _p(dy), _p(x), _p(dx), rows, cols, _p(dbias),
+           L.F32 if dbias.dtype == torch.float32 else L.BF16, int(bool(accumulate)), _p(ws), ws.numel(), _stream())
+    return dx
+
+
 def add(a, b, out=None):
     if out is None: out = torch.empty_like(a)
     L.call("fsb_add", _p(a), _p(b), _p(out), a.numel(), _stream())

@@ -117,6 +117,12 @@ int fsb_glu_bwd(int act, const void* dout, const void* gate, const void* up, voi
                 fsb_stream_t stream);
 int fsb_act_fwd(int act, const void* x, void* y, int64_t n, fsb_stream_t stream);
 int fsb_act_bwd(int act, const void* dy, const void* x, void* dx, int64_t n, fsb_stream_t stream);
+/* dx = dy * act'(x) over contiguous [rows, cols] AND dbias[c] (+)= sum_r dx[r,c] in the same pass: the bias gradient of the
+ * linear layer that produced x (HF GPT2MLP c_fc / BertIntermediate.dense) without a second pass over dx. act 1..3;
+ * workspace: fsb_act_bwd_bias_workspace_bytes(rows, cols). Deterministic. */
+size_t fsb_act_bwd_bias_workspace_bytes(int64_t rows, int64_t cols);
+int fsb_act_bwd_bias(int act, const void* dy, const void* x, void* dx, int64_t rows, int64_t cols, void* dbias,
+                     int dbias_dtype, int accumulate, void* workspace, size_t workspace_bytes, fsb_stream_t stream);
 int fsb_add(const void* a, const void* b, void* out, int64_t n, fsb_stream_t stream);            /* bf16, n % 8 == 0 */
 /* x (bf16, n % 8 == 0) *= *scale_dev; a no-op launch when the device scalar is 1 (upstream gradient of the loss) */
 int fsb_scale_inplace(void* x, int64_t n, const float* scale_dev, fsb_stream_t stream);

@@ -119,6 +119,22 @@ def test_gemm_cta_pair_tiles(layout):
     _close(accb, ref + 1.0, atol=3e-2 * math.sqrt(K / 64), rtol=1e-2, what="pair-tile bf16 accumulate")
 
 
+@pytest.mark.parametrize("act", [L.ACT_GELU_TANH, L.ACT_GELU_ERF, L.ACT_TANH])
+def test_act_bwd_bias_matches_separate_passes(act):
+    rows, cols = 1000, 3072 + 8
+    x, dy = _rand(rows, cols, seed=21), _rand(rows, cols, seed=22)
+    ref_dx = ops.act_bwd(act, dy, x)
+    ref_db = torch.zeros(cols, dtype=torch.float32, device=DEV)
+    ops.colsum(ref_dx, ref_db)
+    db = torch.full((cols,), 3.0, dtype=torch.float32, device=DEV)
+    dx = ops.act_bwd_bias(act, dy, x, db, accumulate=True)
+    assert torch.equal(dx, ref_dx)
+    _close(db, ref_db + 3.0, atol=1e-3, rtol=1e-5, what="fused bias gradient")
+    dbb = torch.zeros(cols, dtype=torch.bfloat16, device=DEV)
+    ops.act_bwd_bias(act, dy, x, dbb)
+    _close(dbb, ref_db, atol=0.3, rtol=1e-2, what="fused bias gradient (bf16 out)")
+
+
 def test_gemm_rejects_bad_arguments():
     a = _rand(64, 60)  # lda = 60 not a multiple of 8
     b = _rand(64, 60)
