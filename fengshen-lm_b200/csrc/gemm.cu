@@ -623,7 +623,8 @@ static int fsb::gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const voi
   const int BN = (force_pair || (N > 128 && tiles256 * 10 >= int64_t(num_sms()) * 7)) ? 256 : 128;
   // CTA pairs (cta_group::2, 256 x 256 tiles) once there is at least one pair tile per SM pair; FSB_GEMM_CTA2=0/1 overrides.
   static const int cta2_env = [] { const char* e = getenv("FSB_GEMM_CTA2"); return e ? atoi(e) : -1; }();
-  const bool cta2 = force_pair || (BN == 256 && tiles256 >= num_sms() && (cta2_env < 0 ? FSB_GEMM_CTA2_DEFAULT : cta2_env != 0));
+  const bool cta2 = force_pair || (BN == 256 && M > GEMM_BM && tiles256 >= num_sms() &&   // (M <= 128: the peer CTA would own no rows)
+                                   (cta2_env < 0 ? FSB_GEMM_CTA2_DEFAULT : cta2_env != 0));
   {
     // A: K-major -> memory [M rows, K inner]; MN-major -> memory [K rows, M inner]
     uint64_t dims[3] = {uint64_t(a_mn ? M : K), uint64_t(a_mn ? K : M), uint64_t(batch)};
