@@ -6,7 +6,7 @@ keeps bf16 activations with fp32 accumulation, the oracle is fp32 end to end):
   loss            |delta| <= 3e-3   at init (north_star asks 1e-3 on the 20-step curve of an fp32/bf16 run; see curve test)
   logits          |delta| <= 4 * 2^-8 * max|logit|
   gradients       cosine >= 0.999 and norm ratio within 2 % per parameter
-  20-step curve   max |delta| <= 2e-2 against the reference curve (bf16 parameters, fp32 master weights)
+  20-step curve   max |delta| <= 1e-2 against the reference curve (measured 3e-3 / 6e-3; bf16 parameters, fp32 master weights)
 """
 import glob
 import math
@@ -90,7 +90,9 @@ def test_loss_curve_vs_reference_golden(path):
         eng.step(lr=O.polynomial_lr(it, lr, warm * steps, steps, lr_end))
         curve.append(out.loss.item())
     err = np.abs(np.array(curve) - g["loss_curve"]).max()
-    assert err <= 2e-2, (err, curve[:3], g["loss_curve"][:3])
+    # measured on B200 (tools/probe_loss_curve.py): 3.0e-3 (hn128; 8.9e-4 relative) and 6.1e-3 (hn64; 2.3e-3 relative) — bf16
+    # parameters / activations against the reference's fp32 CPU run; 1e-2 leaves room for kernel re-tilings
+    assert err <= 1e-2, (err, curve[:3], g["loss_curve"][:3])
 
 
 def test_gradient_accumulation_equals_large_batch():
