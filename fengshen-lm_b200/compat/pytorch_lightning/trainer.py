@@ -48,7 +48,8 @@ class Trainer:
 
     def __init__(self, max_epochs=None, max_steps=-1, gpus=None, devices=None, num_nodes=1, strategy=None,
                  precision="32", accumulate_grad_batches=1, gradient_clip_val=None, default_root_dir=None,
-                 logger=None, callbacks=None, log_every_n_steps=50, replace_sampler_ddp=True, **_):
+                 logger=None, callbacks=None, log_every_n_steps=50, replace_sampler_ddp=True,
+                 resume_from_checkpoint=None, **_):
         self.max_epochs = max_epochs if max_epochs is not None else (1000 if (max_steps or -1) < 0 else -1)
         self.max_steps = max_steps if max_steps is not None else -1
         self.gpus = gpus if gpus is not None else devices
@@ -61,6 +62,7 @@ class Trainer:
         self.callbacks = list(callbacks or [])
         self.log_every_n_steps = log_every_n_steps
         self.replace_sampler_ddp = replace_sampler_ddp
+        self.resume_from_checkpoint = resume_from_checkpoint   # PL-1.x flag: same meaning as fit(ckpt_path=...)
         if isinstance(strategy, str) or strategy is None:
             strategy = strategy_from_string(strategy)
         self.strategy = strategy
@@ -156,8 +158,13 @@ class Trainer:
                                  grad_clip=clip, ga_steps=self.accumulate_grad_batches,
                                  stage=getattr(self.strategy, "stage", 2),
                                  overlap_comm=getattr(self.strategy, "overlap_comm", True))
+        ckpt_path = ckpt_path or self.resume_from_checkpoint
         if ckpt_path:
             self._load_checkpoint(ckpt_path)
+            # the loader built for get_total_steps() (model.setup -> trainer._train_dl()) holds a sampler created with
+            # consumed_samples = 0; rebuild it now that on_load_checkpoint has restored the counter, as PL does
+            if train_dataloaders is None:
+                self._train_loader = None
         for cb in self.callbacks:
             cb.on_fit_start(self, model)
         loader = self._train_dl()
@@ -230,6 +237,8 @@ class Trainer:
         if self.world_size > 1:
             dist.barrier()
         module = self.lightning_module
+        if self.engine is not None:
+            self.engine.wait_params()   # the parameter all-gather of the last step may still be in flight
         consumed = self.global_step * self.accumulate_grad_batches * self.world_size * \
             int(getattr(getattr(self.datamodule, "hparams", {}), "train_batchsize", 1) or 1)
         if self.global_rank == 0:
@@ -258,10 +267,22 @@ class Trainer:
         self.current_epoch = int(state.get("epoch", 0))
         for sc, sd in zip(self.lr_scheduler_configs, state.get("lr_schedulers", [])):
             sc["scheduler"].load_state_dict(sd)
+            # LambdaLR.load_state_dict restores the counters but not optimizer.param_groups[*]['lr'], which is what the
+            # next engine.step() reads: re-derive it from the restored schedule (otherwise the first resumed step runs at
+            # the schedule's step-0 learning rate, 0 under warm-up)
+            last = sc["scheduler"].get_last_lr() if hasattr(sc["scheduler"], "get_last_lr") else None
+            opt = getattr(sc["scheduler"], "optimizer", None)
+            if last is not None and opt is not None:
+                for g, lr in zip(opt.param_groups, last):
+                    g["lr"] = lr
         opt_path = os.path.join(ck, f"zero_pp_rank_{self.global_rank}_mp_rank_00_optim_states.pt")
         if os.path.exists(opt_path):
-            self.engine.load_state_dict(torch.load(opt_path, map_location=fsb_model.flat.params.device,
-                                                   weights_only=False))
+            shard = torch.load(opt_path, map_location=fsb_model.flat.params.device, weights_only=False)
+            if not isinstance(shard, dict) or shard.get("format") != "fsb200-zero-shard-v1":
+                raise RuntimeError(f"{opt_path}: not an fsb200 optimizer shard (format key missing). DeepSpeed's own "
+                                   "zero_pp_rank_* payload cannot be resumed by this engine: load the module weights only "
+                                   "(delete / move the optimizer shard) or resume with the reference stack.")
+            self.engine.load_state_dict(shard)
         else:  # weights-only checkpoint: rebuild the fp32 master copy from the loaded bf16 parameters
             for i in range(len(fsb_model.flat.buckets)):
                 self.engine._seg(self.engine.master, i).copy_(fsb_model.flat.bucket_slice(i, self.engine.rank).float())

@@ -35,6 +35,9 @@ struct AttBwdParams {
   const float* lse;     // [B,H,Sq] log2 domain
   const float* delta;   // [B,H,Sq]
   const uint8_t* kv_mask;
+  const float* rel_bias;     // [nheads, seq_q + seq_kv - 1] additive bias over k - q (natural-log units) or nullptr
+  float* dbias_part;         // per-warp partial diagonal sums of dS written by the dQ kernel (see attn_dbias_reduce_kernel)
+  int64_t dbias_tstride;     // floats per (b, head, q tile, warp): n_all * 64
   const __nv_bfloat16 *q, *dout, *k, *v;   // raw views: at D = 64 each math thread parks its own Q / dO (dQ kernel) or K / V (dKV kernel) row in TMEM as MMA A operands
   int64_t q_row_stride, do_row_stride, k_row_stride, v_row_stride;
   __nv_bfloat16 *dq, *dk, *dv;
@@ -104,7 +107,7 @@ struct AttBwdSmem {
 };
 
 // ================================================================================================ dQ kernel
-template <int D>
+template <int D, bool kBias>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
@@ -260,6 +263,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const float lse = row_ok ? p.lse[stat_idx] : INFINITY;
     const float delta = row_ok ? p.delta[stat_idx] : 0.f;
     const uint8_t* mrow = p.kv_mask ? p.kv_mask + int64_t(b) * p.seq_kv : nullptr;
+    // relative-position bias (mT5): this row reads entries (c0 + c - q_row + seq_q - 1) of its head's vector
+    const int n_rel = p.seq_q + p.seq_kv - 1;
+    const float* brow = kBias ? p.rel_bias + int64_t(head) * n_rel + (p.seq_q - 1 - min(q_row, p.seq_q - 1)) : nullptr;
+    float* dpart = kBias && p.dbias_part
+                       ? p.dbias_part + (((int64_t(b) * p.nheads + head) * gridDim.x + tile) * (AB_MATH / 32) + warp) * p.dbias_tstride
+                       : nullptr;
     if constexpr (kQT) {  // park this thread's quarter of its Q and dO rows in TMEM (bf16 pairs, column = d / 2): the A operands of S and dP
       constexpr int W = D / 2 / AB_PARTS;   // 32-bit words per thread: 8 (D = 64) or 16 (D = 128)
       uint32_t wq[W], wd[W];
@@ -294,12 +303,21 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int c0 = j * AB_BN + part * AB_PC;
       const bool need_mask = (p.causal && j * AB_BN + AB_BN - 1 > q0) || (j * AB_BN + AB_BN > p.seq_kv) || mrow;
       uint32_t pk[AB_PC / 2];
+      [[maybe_unused]] float bl[AB_PC];   // bias of this thread's columns, log2 domain
+      [[maybe_unused]] float ds[AB_PC];   // dS in fp32 (for the bias gradient)
+      if constexpr (kBias) {
+        constexpr float kLog2e = 1.4426950408889634f;
+#pragma unroll
+        for (int c = 0; c < AB_PC; ++c) bl[c] = __ldg(brow + min(c0 + c, p.seq_kv - 1)) * kLog2e;
+      }
       if (!need_mask) {
 #pragma unroll
         for (int c = 0; c < AB_PC; c += 2) {
-          const float p0 = ex2_approx(__uint_as_float(s[c]) * p.scale_log2 - lse);
-          const float p1 = ex2_approx(__uint_as_float(s[c + 1]) * p.scale_log2 - lse);
-          pk[c >> 1] = pack_bf16x2(p0 * (__uint_as_float(d[c]) - delta), p1 * (__uint_as_float(d[c + 1]) - delta));
+          float x0 = __uint_as_float(s[c]) * p.scale_log2 - lse, x1 = __uint_as_float(s[c + 1]) * p.scale_log2 - lse;
+          if constexpr (kBias) { x0 += bl[c]; x1 += bl[c + 1]; }
+          const float d0 = ex2_approx(x0) * (__uint_as_float(d[c]) - delta), d1 = ex2_approx(x1) * (__uint_as_float(d[c + 1]) - delta);
+          if constexpr (kBias) { ds[c] = d0; ds[c + 1] = d1; }
+          pk[c >> 1] = pack_bf16x2(d0, d1);
         }
       } else {
 #pragma unroll
@@ -310,9 +328,35 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const int col = c0 + c + e;
             bool keep = col < p.seq_kv && !(p.causal && col > q_row);
             if (keep && mrow) keep = mrow[col] != 0;
-            pv[e] = keep ? ex2_approx(__uint_as_float(s[c + e]) * p.scale_log2 - lse) : 0.f;
+            float x = __uint_as_float(s[c + e]) * p.scale_log2 - lse;
+            if constexpr (kBias) x += bl[c + e];
+            pv[e] = keep ? ex2_approx(x) : 0.f;
           }
-          pk[c >> 1] = pack_bf16x2(pv[0] * (__uint_as_float(d[c]) - delta), pv[1] * (__uint_as_float(d[c + 1]) - delta));
+          const float d0 = pv[0] * (__uint_as_float(d[c]) - delta), d1 = pv[1] * (__uint_as_float(d[c + 1]) - delta);
+          if constexpr (kBias) { ds[c] = d0; ds[c + 1] = d1; }
+          pk[c >> 1] = pack_bf16x2(d0, d1);
+        }
+      }
+      if constexpr (kBias) {
+        // Bias gradient: dBias[h, r] = sum over (b, q) of dS[q, q + r]. Sum this warp's 32 rows x 16 columns along the
+        // diagonals with a systolic shuffle (A_c[l] = dS[l][c] + A_{c-1}[l-1]): after column c the value leaving lane 31 is
+        // the finished diagonal c - 32, after the last column lane l holds diagonal 15 - l. The 47 sums go to this warp's
+        // private slice of the workspace (slot = diagonal + 31 of step j; steps do not overlap: 47 < 64), plain stores, no
+        // atomics — attn_dbias_reduce_kernel adds the slices up in a fixed order.
+        if (dpart != nullptr) {
+          float A = 0.f, E[AB_PC];
+#pragma unroll
+          for (int c = 0; c < AB_PC; ++c) {
+            const float t = __shfl_sync(0xffffffffu, A, (lane + 31) & 31);
+            E[c] = t;
+            A = ds[c] + (lane == 0 ? 0.f : t);
+          }
+          float* dst = dpart + int64_t(j) * 64;
+          dst[46 - lane] = A;
+          if (lane == 0) {
+#pragma unroll
+            for (int c = 1; c < AB_PC; ++c) dst[c - 1] = E[c];
+          }
         }
       }
       tmem_st8(t_lane + TM_S + buf * 128 + part * AB_PC, pk);   // dS(j) over the S(j) columns this thread has consumed
@@ -356,7 +400,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ================================================================================================ dK / dV kernel
-template <int D>
+template <int D, bool kBias>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                     const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
@@ -506,6 +550,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
     if (row_ok && p.kv_mask) row_ok = p.kv_mask[int64_t(b) * p.seq_kv + kv_row] != 0;
     const int64_t stat_base = (int64_t(b) * p.nheads + head) * p.seq_q;
     const bool vec_stats = (p.seq_q % 4) == 0;   // 16-byte aligned rows of lse / delta
+    // relative-position bias: key row kv_row, query column qi -> entry (kv_row - qi + seq_q - 1) of the head's vector
+    const int n_rel = p.seq_q + p.seq_kv - 1;
+    const float* bkey = kBias ? p.rel_bias + int64_t(head) * n_rel + (min(kv_row, p.seq_kv - 1) + p.seq_q - 1) : nullptr;
     if constexpr (kKT) {  // park this thread's quarter of its K and V rows in TMEM (A operands of S^T and dP^T)
       constexpr int W = D / 2 / AB_PARTS;
       uint32_t wk[W], wv[W];
@@ -562,7 +609,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
         float pv[2], dv[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          float x = ex2_approx(__uint_as_float(s[c + e]) * p.scale_log2 - lse_c[c + e]);
+          float arg = __uint_as_float(s[c + e]) * p.scale_log2 - lse_c[c + e];
+          if constexpr (kBias) arg += __ldg(bkey - min(qc0 + c + e, p.seq_q - 1)) * 1.4426950408889634f;
+          float x = ex2_approx(arg);
           const bool keep = row_ok && !(need_causal && (qc0 + c + e) < kv_row);
           x = keep ? x : 0.f;
           pv[e] = x;
@@ -619,16 +668,60 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_consta
   }
 }
 
-template <int D>
+// dBias[h, i] (+)= sum over (b, q tile, warp) of the per-warp diagonal sums the dQ kernel left in the workspace, in a FIXED
+// order (deterministic). i = (k - q) + seq_q - 1. Stage 1: grid (i chunks, heads, batch splits) -> part2[split][h][i];
+// stage 2 adds the splits onto the caller's fp32 vector.
+__global__ void __launch_bounds__(128) attn_dbias_reduce_kernel(const float* __restrict__ part, float* __restrict__ part2,
+                                                                int batch, int nheads, int seq_q, int seq_kv, int causal,
+                                                                int n_qtiles, int64_t tstride, int bsplit) {
+  const int n_rel = seq_q + seq_kv - 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = blockIdx.y, sp = blockIdx.z;
+  if (i >= n_rel) return;
+  const int d = i - (seq_q - 1);
+  const int n_all = (seq_kv + AB_BN - 1) / AB_BN;
+  const int b0 = int(int64_t(batch) * sp / bsplit), b1 = int(int64_t(batch) * (sp + 1) / bsplit);
+  float acc = 0.f;
+  for (int b = b0; b < b1; ++b) {
+    for (int tile = 0; tile < n_qtiles; ++tile) {
+      const int q0 = tile * AB_BM;
+      const int n_steps = causal ? min(n_all, (min(q0 + AB_BM, seq_q) + AB_BN - 1) / AB_BN) : n_all;
+      const float* base = part + ((int64_t(b) * nheads + h) * n_qtiles + tile) * (AB_MATH / 32) * tstride;
+#pragma unroll 4
+      for (int w = 0; w < AB_MATH / 32; ++w) {
+        const int quad = w & 3, prt = w >> 2;
+        const int t = d + q0 + quad * 32 - prt * AB_PC + 31;
+        if (t >= 0 && (t & 63) < 47 && (t >> 6) < n_steps) acc += base[int64_t(w) * tstride + t];
+      }
+    }
+  }
+  part2[(int64_t(sp) * nheads + h) * n_rel + i] = acc;
+}
+__global__ void __launch_bounds__(128) attn_dbias_final_kernel(const float* __restrict__ part2, float* __restrict__ dbias,
+                                                               int nheads, int n_rel, int bsplit) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = blockIdx.y;
+  if (i >= n_rel) return;
+  float acc = dbias[int64_t(h) * n_rel + i];
+  for (int sp = 0; sp < bsplit; ++sp) acc += part2[(int64_t(sp) * nheads + h) * n_rel + i];
+  dbias[int64_t(h) * n_rel + i] = acc;
+}
+static inline int dbias_bsplit(int batch) { return batch < 16 ? batch : 16; }
+static inline size_t dbias_part_floats(int64_t batch, int64_t seq_q, int64_t seq_kv, int nheads) {
+  const int64_t n_qt = (seq_q + AB_BM - 1) / AB_BM, n_all = (seq_kv + AB_BN - 1) / AB_BN;
+  return size_t(batch) * nheads * n_qt * (AB_MATH / 32) * n_all * 64;
+}
+
+template <int D, bool kBias>
 static int launch_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
                            int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, int64_t do_rs, int64_t o_hs,
-                           float* delta, AttBwdParams& p, cudaStream_t st) {
+                           float* delta, AttBwdParams& p, float* drel_bias, float* part2, cudaStream_t st) {
   using SQ = AttBwdSmem<D, (D == 64 ? 6 : 4), 2>;
   using SK = AttBwdSmem<D, (D == 64 ? 6 : 3), 4>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ::TOTAL);
-    cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK::TOTAL);
+    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_kernel<D, kBias>, cudaFuncAttributeMaxDynamicSharedMemorySize, SQ::TOTAL);
+    cudaError_t e2 = cudaFuncSetAttribute(attn_bwd_dkv_kernel<D, kBias>, cudaFuncAttributeMaxDynamicSharedMemorySize, SK::TOTAL);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
       set_error("sdpa_bwd: cudaFuncSetAttribute(%d / %d) failed", SQ::TOTAL, SK::TOTAL);
       return FSB_ERR_CUDA;
@@ -659,13 +752,21 @@ static int launch_attn_bwd(const void* q, const void* k, const void* v, const vo
   // 2. dQ
   {
     dim3 grid((p.seq_q + AB_BM - 1) / AB_BM, p.nheads, p.batch);
-    attn_bwd_dq_kernel<D><<<grid, AB_THREADS, SQ::TOTAL, st>>>(tq128, tdo128, tk64, tv64, p);
+    attn_bwd_dq_kernel<D, kBias><<<grid, AB_THREADS, SQ::TOTAL, st>>>(tq128, tdo128, tk64, tv64, p);
     FSB_CUDA_LAUNCH_CHECK();
+    if (kBias && drel_bias != nullptr) {
+      const int n_rel = p.seq_q + p.seq_kv - 1, bs = dbias_bsplit(p.batch);
+      attn_dbias_reduce_kernel<<<dim3((n_rel + 127) / 128, p.nheads, bs), 128, 0, st>>>(
+          p.dbias_part, part2, p.batch, p.nheads, p.seq_q, p.seq_kv, p.causal, int(grid.x), p.dbias_tstride, bs);
+      FSB_CUDA_LAUNCH_CHECK();
+      attn_dbias_final_kernel<<<dim3((n_rel + 127) / 128, p.nheads), 128, 0, st>>>(part2, drel_bias, p.nheads, n_rel, bs);
+      FSB_CUDA_LAUNCH_CHECK();
+    }
   }
   // 3. dK, dV
   {
     dim3 grid((p.seq_kv + AB_BM - 1) / AB_BM, p.nheads, p.batch);
-    attn_bwd_dkv_kernel<D><<<grid, AB_THREADS, SK::TOTAL, st>>>(tk128, tv128, tq64, tdo64, p);
+    attn_bwd_dkv_kernel<D, kBias><<<grid, AB_THREADS, SK::TOTAL, st>>>(tk128, tv128, tq64, tdo64, p);
     FSB_CUDA_LAUNCH_CHECK();
   }
   return FSB_OK;
@@ -688,7 +789,8 @@ extern "C" int fsb_sdpa_bwd(const void* q, const void* k, const void* v, const v
                             int64_t dk_row_stride, int64_t dv_row_stride, int64_t q_head_stride, int64_t k_head_stride,
                             int64_t v_head_stride, int64_t o_head_stride, int64_t do_head_stride,
                             int64_t dq_head_stride, int64_t dk_head_stride, int64_t dv_head_stride, float scale,
-                            int causal, const uint8_t* kv_mask, fsb_stream_t st) {
+                            int causal, const uint8_t* kv_mask, const float* rel_bias, float* drel_bias, void* workspace,
+                            size_t workspace_bytes, fsb_stream_t st) {
   FSB_REQUIRE(q && k && v && o && dout && lse && delta && dq && dk && dv, "sdpa_bwd: null pointer");
   FSB_REQUIRE(head_dim == 64 || head_dim == 128, "sdpa_bwd: head_dim %d unsupported (64 or 128)", head_dim);
   FSB_REQUIRE(batch > 0 && seq_q > 0 && seq_kv > 0 && nheads > 0 && batch < 65536 && nheads < 65536, "sdpa_bwd: bad dims");
@@ -700,8 +802,19 @@ extern "C" int fsb_sdpa_bwd(const void* q, const void* k, const void* v, const v
                dk_row_stride | dv_row_stride | q_head_stride | k_head_stride | v_head_stride | o_head_stride |
                do_head_stride | dq_head_stride | dk_head_stride | dv_head_stride) % 8 == 0,
               "sdpa_bwd: strides must be multiples of 8 elements");
+  FSB_REQUIRE(drel_bias == nullptr || rel_bias != nullptr, "sdpa_bwd: drel_bias without rel_bias");
   AttBwdParams p;
   p.lse = lse; p.delta = delta; p.kv_mask = kv_mask;
+  p.rel_bias = rel_bias; p.dbias_part = nullptr; p.dbias_tstride = ((seq_kv + AB_BN - 1) / AB_BN) * 64;
+  float* part2 = nullptr;
+  if (drel_bias != nullptr) {
+    const size_t need = fsb_sdpa_bwd_workspace_bytes(batch, seq_q, seq_kv, nheads);
+    FSB_REQUIRE(workspace != nullptr && workspace_bytes >= need && aligned16(workspace),
+                "sdpa_bwd: the bias gradient needs a %zu-byte workspace (fsb_sdpa_bwd_workspace_bytes); got %zu", need,
+                workspace_bytes);
+    p.dbias_part = static_cast<float*>(workspace);
+    part2 = p.dbias_part + dbias_part_floats(batch, seq_q, seq_kv, nheads);
+  }
   p.q = (const __nv_bfloat16*)q; p.dout = (const __nv_bfloat16*)dout; p.q_row_stride = q_row_stride; p.do_row_stride = do_row_stride;
   p.k = (const __nv_bfloat16*)k; p.v = (const __nv_bfloat16*)v; p.k_row_stride = k_row_stride; p.v_row_stride = v_row_stride;
   p.dq = (__nv_bfloat16*)dq; p.dk = (__nv_bfloat16*)dk; p.dv = (__nv_bfloat16*)dv;
@@ -711,9 +824,17 @@ extern "C" int fsb_sdpa_bwd(const void* q, const void* k, const void* v, const v
   p.do_head_stride = int(do_head_stride);
   p.seq_q = int(seq_q); p.seq_kv = int(seq_kv); p.nheads = nheads; p.batch = int(batch); p.causal = causal;
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
-  if (head_dim == 128)
-    return launch_attn_bwd<128>(q, k, v, o, dout, q_row_stride, k_row_stride, v_row_stride, o_row_stride, do_row_stride,
-                                o_head_stride, delta, p, (cudaStream_t)st);
-  return launch_attn_bwd<64>(q, k, v, o, dout, q_row_stride, k_row_stride, v_row_stride, o_row_stride, do_row_stride,
-                             o_head_stride, delta, p, (cudaStream_t)st);
+#define FSB_BWD(DD, BB)                                                                                                  \
+  launch_attn_bwd<DD, BB>(q, k, v, o, dout, q_row_stride, k_row_stride, v_row_stride, o_row_stride, do_row_stride,       \
+                          o_head_stride, delta, p, drel_bias, part2, (cudaStream_t)st)
+  if (rel_bias != nullptr) return head_dim == 128 ? FSB_BWD(128, true) : FSB_BWD(64, true);
+  return head_dim == 128 ? FSB_BWD(128, false) : FSB_BWD(64, false);
+#undef FSB_BWD
+}
+
+extern "C" size_t fsb_sdpa_bwd_workspace_bytes(int64_t batch, int64_t seq_q, int64_t seq_kv, int nheads) {
+  if (batch <= 0 || seq_q <= 0 || seq_kv <= 0 || nheads <= 0) return 0;
+  // per-warp diagonal sums of the dQ kernel + the batch-split partial vectors of the reduction
+  return (fsb::dbias_part_floats(batch, seq_q, seq_kv, nheads) +
+          size_t(fsb::dbias_bsplit(int(batch))) * nheads * size_t(seq_q + seq_kv - 1)) * sizeof(float);
 }

@@ -51,6 +51,7 @@ struct AttFwdParams {
   __nv_bfloat16* o;
   float* lse;               // [batch, nheads, seq_q], log2 domain
   const uint8_t* kv_mask;   // [batch, seq_kv] (1 = attend) or nullptr
+  const float* rel_bias;    // [nheads, seq_q + seq_kv - 1] additive bias over the offset k - q (natural-log units) or nullptr
   int64_t o_row_stride, o_head_stride;
   int q_head_stride, k_head_stride, v_head_stride;
   int seq_q, seq_kv, nheads, batch;
@@ -66,7 +67,7 @@ __device__ long long g_fwd_trace[2][64][8];
 #define FTRACE(role, step, k) do { } while (0)
 #endif
 
-template <int D>
+template <int D, bool kBias>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttFwdParams p) {
@@ -239,6 +240,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int sw = r_in & 7;
     const uint8_t* mrow = p.kv_mask ? p.kv_mask + int64_t(b) * p.seq_kv : nullptr;
     const float sc = p.scale_log2;
+    // T5 / mT5 relative-position bias (transformers mt5/modeling_mt5.py:181-235,:320): bias[h, q, k] depends on k - q only, so it
+    // arrives as one vector per head; this row reads the 64 consecutive entries starting at (c0 - q_row + seq_q - 1).
+    const int n_rel = p.seq_q + p.seq_kv - 1;
+    const float* brow = kBias ? p.rel_bias + int64_t(head) * n_rel + (p.seq_q - 1 - min(q_row, p.seq_q - 1)) : nullptr;
+    const float sc_eff = kBias ? 1.f : sc;        // with a bias the scores are moved to the scaled log2 domain first
 
     float m_ref = -INFINITY;                      // exponent reference, scaled log2 domain
     float l0 = 0.f, l1 = 0.f;                     // two partial row sums (shorter FADD chains)
@@ -257,6 +263,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();                             // S(j) is in cur[]
       FTRACE(0, j, 1);
       const int c0 = j * ATT_BKV;
+      if constexpr (kBias) {
+        constexpr float kLog2e = 1.4426950408889634f;
+        if (c0 + ATT_BKV <= p.seq_kv) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            cur[c] = __float_as_uint(fmaf(__ldg(brow + c0 + c), kLog2e, __uint_as_float(cur[c]) * sc));
+        } else {   // last, partial key tile: stay inside the vector (those columns are masked below anyway)
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            cur[c] = __float_as_uint(fmaf(__ldg(brow + min(c0 + c, p.seq_kv - 1)), kLog2e, __uint_as_float(cur[c]) * sc));
+        }
+      }
       const bool need_mask = (p.causal && c0 + ATT_BKV - 1 > q0 + slot * ATT_BQ) || (c0 + ATT_BKV > p.seq_kv) || mrow;
       if (need_mask) {
 #pragma unroll
@@ -273,7 +291,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int e = 0; e < 4; ++e) mx4[e] = fmaxf(mx4[e], __uint_as_float(cur[c + e]));
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sc;   // scale > 0 (checked on the host)
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * sc_eff;   // scale > 0 (checked on the host)
       FTRACE(0, j, 2);
       // lazy reference update: raise m_ref only when the row max outgrew it by more than 2^tau
       const bool raise = mx > m_ref + ATT_RESCALE_TAU;
@@ -308,8 +326,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float a = ex2_approx(fmaf(__uint_as_float(cur[ch * 8 + 2 * e]), sc, neg_m));
-          const float bq = ex2_approx(fmaf(__uint_as_float(cur[ch * 8 + 2 * e + 1]), sc, neg_m));
+          const float a = ex2_approx(fmaf(__uint_as_float(cur[ch * 8 + 2 * e]), sc_eff, neg_m));
+          const float bq = ex2_approx(fmaf(__uint_as_float(cur[ch * 8 + 2 * e + 1]), sc_eff, neg_m));
           pk[e] = pack_bf16x2(a, bq);
           l0 += a; l1 += bq;                      // fp32 sums of the unrounded probabilities (LSE exact to fp32)
         }
@@ -371,12 +389,12 @@ int make_attn_tmap(CUtensorMap* tm, const void* base, int64_t row_stride, int64_
   return make_tmap_bf16(tm, base, 3, dims, strides, box);
 }
 
-template <int D>
+template <int D, bool kBias>
 static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttFwdParams& p,
                            cudaStream_t st) {
   using S = AttFwdSmem<D>;
   static bool configured = false;
-  auto kern = attn_fwd_kernel<D>;
+  auto kern = attn_fwd_kernel<D, kBias>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) {
@@ -405,7 +423,7 @@ extern "C" int fsb_sdpa_fwd(const void* q, const void* k, const void* v, void* o
                             int64_t seq_q, int64_t seq_kv, int nheads, int head_dim, int64_t q_row_stride,
                             int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride, int64_t q_head_stride,
                             int64_t k_head_stride, int64_t v_head_stride, int64_t o_head_stride, float scale, int causal,
-                            const uint8_t* kv_mask, fsb_stream_t st) {
+                            const uint8_t* kv_mask, const float* rel_bias, fsb_stream_t st) {
   FSB_REQUIRE(q && k && v && o && lse, "sdpa_fwd: null pointer");
   FSB_REQUIRE(head_dim == 64 || head_dim == 128, "sdpa_fwd: head_dim %d unsupported (64 or 128)", head_dim);
   FSB_REQUIRE(batch > 0 && seq_q > 0 && seq_kv > 0 && nheads > 0 && batch < 65536 && nheads < 65536, "sdpa_fwd: bad dims");
@@ -421,12 +439,15 @@ extern "C" int fsb_sdpa_fwd(const void* q, const void* k, const void* v, void* o
   if ((rc = make_attn_tmap(&tk, k, k_row_stride, (nheads - 1) * k_head_stride + head_dim, seq_kv, batch, ATT_BKV))) return rc;
   if ((rc = make_attn_tmap(&tv, v, v_row_stride, (nheads - 1) * v_head_stride + head_dim, seq_kv, batch, ATT_BKV))) return rc;
   AttFwdParams p;
-  p.o = (__nv_bfloat16*)o; p.lse = lse; p.kv_mask = kv_mask;
+  p.o = (__nv_bfloat16*)o; p.lse = lse; p.kv_mask = kv_mask; p.rel_bias = rel_bias;
   p.o_row_stride = o_row_stride; p.o_head_stride = o_head_stride;
   p.q_head_stride = int(q_head_stride); p.k_head_stride = int(k_head_stride); p.v_head_stride = int(v_head_stride);
   p.seq_q = int(seq_q); p.seq_kv = int(seq_kv); p.nheads = nheads; p.batch = int(batch);
   p.causal = causal;
   p.scale_log2 = scale * 1.4426950408889634f;
-  return head_dim == 128 ? launch_attn_fwd<128>(tq, tk, tv, p, (cudaStream_t)st)
-                         : launch_attn_fwd<64>(tq, tk, tv, p, (cudaStream_t)st);
+  if (rel_bias != nullptr)
+    return head_dim == 128 ? launch_attn_fwd<128, true>(tq, tk, tv, p, (cudaStream_t)st)
+                           : launch_attn_fwd<64, true>(tq, tk, tv, p, (cudaStream_t)st);
+  return head_dim == 128 ? launch_attn_fwd<128, false>(tq, tk, tv, p, (cudaStream_t)st)
+                         : launch_attn_fwd<64, false>(tq, tk, tv, p, (cudaStream_t)st);
 }

@@ -26,7 +26,7 @@ static int ew_grid(int64_t work_items, int threads) {
 __global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ cos_t,
                                                    const float* __restrict__ sin_t, const int64_t* __restrict__ pos,
                                                    int64_t rows, int nheads, int D, int64_t row_stride,
-                                                   int64_t head_stride, float sign) {
+                                                   int64_t head_stride, float sign, int64_t max_pos) {
   const int half = D >> 1;
   const int vec_per_head = half >> 3;  // 8 pairs per thread-iteration
   const int64_t total = rows * nheads * vec_per_head;
@@ -37,6 +37,14 @@ __global__ void __launch_bounds__(256) rope_kernel(__nv_bfloat16* __restrict__ x
     const int64_t t = th / nheads;
     const int64_t p = pos[t];
     __nv_bfloat16* base = x + t * row_stride + h * head_stride + v * 8;
+    if (p < 0 || p >= max_pos) {
+      // a position outside the cos/sin table (the reference regrows its cache, positional_embeddings.py:54-68; the host
+      // wrapper sizes the table and validates position_ids): never read out of bounds — poison the row so the loss is NaN
+      const uint32_t nan2 = 0x7fc07fc0u;
+      *reinterpret_cast<uint4*>(base) = make_uint4(nan2, nan2, nan2, nan2);
+      *reinterpret_cast<uint4*>(base + half) = make_uint4(nan2, nan2, nan2, nan2);
+      continue;
+    }
     float a[8], b[8], c[8], s[8];
     unpack8(*reinterpret_cast<const uint4*>(base), a);
     unpack8(*reinterpret_cast<const uint4*>(base + half), b);
@@ -358,9 +366,86 @@ __global__ void __launch_bounds__(256) embedding_bwd_kernel(const int64_t* __res
   }
 }
 
+
+// Deterministic embedding backward. `ids_sorted` / `order` are the token ids sorted ascending (stable) and the token index
+// of each sorted position. One CTA per sorted position; only the CTA at the START of a run of equal ids works: it sums the
+// run's dout rows in fp32 — EMB_R occurrences in flight (occurrence j goes to sub-sum j % EMB_R), combined in a fixed order —
+// and adds the total onto dW[id] with ONE bf16 rounding. torch's embedding backward (what the reference runs) accumulates
+// in fp32 as well; the former bf16x2 atomics rounded after every occurrence and depended on the atomic order.
+constexpr int EMB_R = 4;
+__global__ void __launch_bounds__(256) embedding_bwd_sorted_kernel(const int64_t* __restrict__ ids_sorted,
+                                                                   const int64_t* __restrict__ order,
+                                                                   const __nv_bfloat16* __restrict__ dout,
+                                                                   __nv_bfloat16* __restrict__ dW, int64_t rows, int cols) {
+  const int64_t i0 = blockIdx.x;
+  const int64_t id = ids_sorted[i0];
+  if (i0 > 0 && ids_sorted[i0 - 1] == id) return;   // not the start of a run
+  __shared__ float red[EMB_R][64 * 8];
+  const int lane_c = threadIdx.x & 63, r = threadIdx.x >> 6;   // 64 column vectors x EMB_R occurrences in flight
+  const int vpr = cols >> 3;
+  for (int cv0 = 0; cv0 < vpr; cv0 += 64) {
+    const int cv = cv0 + lane_c;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (cv < vpr) {
+      for (int64_t j = i0 + r; j < rows && ids_sorted[j] == id; j += EMB_R) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(dout + order[j] * cols + cv * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[r][lane_c * 8 + e] = acc[e];
+    __syncthreads();
+    if (r == 0 && cv < vpr) {
+      float f[8];
+      __nv_bfloat16* dst = dW + id * cols + cv * 8;
+      unpack8(*reinterpret_cast<const uint4*>(dst), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float t = red[0][lane_c * 8 + e];
+#pragma unroll
+        for (int q = 1; q < EMB_R; ++q) t += red[q][lane_c * 8 + e];
+        f[e] += t;
+      }
+      *reinterpret_cast<uint4*>(dst) = pack8(f);
+    }
+  }
+}
+
+// out (bf16) = in (fp32), 8 elements per thread-iteration
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                            int64_t n8) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n8; i += int64_t(gridDim.x) * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(in)[2 * i], b = reinterpret_cast<const float4*>(in)[2 * i + 1];
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    reinterpret_cast<uint4*>(out)[i] = pack8(f);
+  }
+}
+
 }  // namespace fsb
 
 using namespace fsb;
+
+extern "C" int fsb_embedding_bwd_sorted(const int64_t* ids_sorted, const int64_t* order, const void* dout, void* dW,
+                                        int64_t rows, int64_t cols, fsb_stream_t st) {
+  FSB_REQUIRE(ids_sorted && order && dout && dW && rows > 0 && cols > 0 && cols % 8 == 0, "embedding_bwd_sorted: bad args");
+  FSB_REQUIRE(rows < (int64_t(1) << 31), "embedding_bwd_sorted: too many rows");
+  FSB_REQUIRE(aligned16(dout) && aligned16(dW), "embedding_bwd_sorted: alignment");
+  embedding_bwd_sorted_kernel<<<unsigned(rows), 256, 0, (cudaStream_t)st>>>(
+      ids_sorted, order, (const __nv_bfloat16*)dout, (__nv_bfloat16*)dW, rows, int(cols));
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
+
+extern "C" int fsb_cast_f32_to_bf16(const float* in, void* out, int64_t n, fsb_stream_t st) {
+  FSB_REQUIRE(in && out && n > 0 && n % 8 == 0, "cast_f32_to_bf16: n must be a positive multiple of 8");
+  FSB_REQUIRE(aligned16(in) && aligned16(out), "cast_f32_to_bf16: alignment");
+  cast_f32_bf16_kernel<<<ew_grid(n / 8, 256), 256, 0, (cudaStream_t)st>>>(in, (__nv_bfloat16*)out, n / 8);
+  FSB_CUDA_LAUNCH_CHECK();
+  return FSB_OK;
+}
 
 extern "C" int fsb_rope_inplace(void* x, const float* cos_table, const float* sin_table, const int64_t* positions,
                                 int64_t rows, int nheads, int head_dim, int64_t row_stride, int64_t head_stride,
@@ -369,11 +454,11 @@ extern "C" int fsb_rope_inplace(void* x, const float* cos_table, const float* si
   FSB_REQUIRE(rows > 0 && nheads > 0 && head_dim % 16 == 0 && head_dim > 0, "rope: head_dim must be a multiple of 16");
   FSB_REQUIRE(row_stride % 8 == 0 && head_stride % 8 == 0 && aligned16(x) && aligned16(cos_table) && aligned16(sin_table),
               "rope: alignment");
-  (void)max_pos;
+  FSB_REQUIRE(max_pos > 0, "rope: max_pos (rows of the cos/sin tables) must be positive");
   const int64_t total = rows * nheads * (head_dim / 16);
   rope_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)st>>>((__nv_bfloat16*)x, cos_table, sin_table, positions, rows,
                                                                nheads, head_dim, row_stride, head_stride,
-                                                               backward ? -1.f : 1.f);
+                                                               backward ? -1.f : 1.f, max_pos);
   FSB_CUDA_LAUNCH_CHECK();
   return FSB_OK;
 }

@@ -469,6 +469,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// SMs left to concurrently running communication kernels (fsb_set_reserved_sms): a persistent GEMM CTA fills an SM
+// (all of its registers), so a collective that overlaps backward would otherwise push GEMM CTAs into a second wave.
+static int g_reserved_sms = 0;
+static inline int gemm_sms(bool pairs) {
+  // a blocked SM blocks its whole CTA pair: pair kernels give up two SMs per reserved one
+  const int n = num_sms() - (pairs ? 2 : 1) * g_reserved_sms;
+  return n < 2 ? 2 : n;
+}
+
 template <int kLayout, int BN, bool kAux, bool kCta2>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD, const CUtensorMap& tmAux,
                        const GemmParams& p, cudaStream_t stream) {
@@ -485,7 +494,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   }
   const int num_tiles = p.tiles_m * p.tiles_n * p.batch;
   if constexpr (kCta2) {
-    const int pairs = num_sms() / 2;
+    const int pairs = gemm_sms(true) / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * (num_tiles < pairs ? num_tiles : pairs));
     cfg.blockDim = dim3(GEMM_THREADS);
@@ -501,7 +510,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
       return FSB_ERR_CUDA;
     }
   } else {
-    const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+    const int grid = num_tiles < gemm_sms(false) ? num_tiles : gemm_sms(false);
     kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, tmD, tmAux, p);
   }
   FSB_CUDA_LAUNCH_CHECK();
@@ -534,22 +543,6 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, i
   }
 }
 
-// Scratch for split-K partial products: one lazily grown buffer per device. fsb_gemm_bf16 calls that split K must not run
-// concurrently on several streams of the same device (the training step issues all GEMMs on one stream).
-static void* g_splitk_ws[16] = {};
-static size_t g_splitk_bytes[16] = {};
-static float* splitk_workspace(size_t bytes) {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-  if (g_splitk_bytes[dev] < bytes) {
-    if (g_splitk_ws[dev]) { cudaDeviceSynchronize(); cudaFree(g_splitk_ws[dev]); }
-    g_splitk_ws[dev] = nullptr; g_splitk_bytes[dev] = 0;
-    if (cudaMalloc(&g_splitk_ws[dev], bytes) != cudaSuccess) return nullptr;
-    g_splitk_bytes[dev] = bytes;
-  }
-  return static_cast<float*>(g_splitk_ws[dev]);
-}
-
 static int gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                      int64_t ldb, void* D, int64_t ldd, int d_dtype, const void* bias, int bias_dtype,
                      int epilogue, int accumulate, void* aux, int64_t ldaux, int64_t batch, int64_t stride_a,
@@ -559,26 +552,53 @@ static int gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const void* A,
 
 using namespace fsb;
 
+extern "C" int fsb_set_reserved_sms(int n) {
+  FSB_REQUIRE(n >= 0 && n <= 64, "set_reserved_sms: %d out of range [0, 64]", n);
+  fsb::g_reserved_sms = n;
+  return FSB_OK;
+}
+
+// Split-K plan for weight-gradient GEMMs whose output has too few tiles to occupy the SMs (e.g. 768 x 768 x 32768: 36
+// tiles): `splits` K-chunks run as a batched GEMM into an fp32 scratch and are summed in a fixed order (deterministic).
+// Preferred: 256 x 256 CTA-pair tiles (a lone 128 x 128 tile is shared-memory-bound at half the MMA rate), K split so that the
+// SM pairs are busy; small outputs (M or N < 256) keep 128 x 128 tiles. Returns 0 / 1 when the call does not split.
+static int splitk_plan(int layout, int64_t M, int64_t N, int64_t K, int64_t batch, bool plain, bool* pair_out) {
+  if (!(layout == FSB_GEMM_TN && batch == 1 && plain && M > 0 && N > 0 && N % 4 == 0 && (M * N) % 8 == 0 && K >= 4096)) return 0;
+  const bool pair = M >= 256 && N >= 256;
+  const int64_t tiles = pair ? ((M + 255) / 256) * ((N + 255) / 256) : ((M + GEMM_BM - 1) / GEMM_BM) * ((N + 127) / 128);
+  const int64_t slots = pair ? num_sms() / 2 : num_sms();
+  int splits = int(slots / tiles);
+  if (splits > 16) splits = 16;
+  while (splits > 1 && (K % (int64_t(splits) * GEMM_BK) != 0 || K / splits < 1024)) --splits;
+  if (pair_out) *pair_out = pair;
+  return (splits >= 2 && tiles * 2 <= slots) ? splits : 0;
+}
+
+extern "C" size_t fsb_gemm_workspace_bytes(int layout, int64_t M, int64_t N, int64_t K) {
+  const int splits = splitk_plan(layout, M, N, K, 1, true, nullptr);
+  return splits ? size_t(splits) * size_t(M) * size_t(N) * sizeof(float) : 0;
+}
+
 extern "C" int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
                              int64_t ldb, void* D, int64_t ldd, int d_dtype, const void* bias, int bias_dtype,
                              int epilogue, int accumulate, void* aux, int64_t ldaux, int64_t batch, int64_t stride_a,
-                             int64_t stride_b, int64_t stride_d, int64_t stride_aux, fsb_stream_t stream_) {
+                             int64_t stride_b, int64_t stride_d, int64_t stride_aux, void* workspace,
+                             size_t workspace_bytes, fsb_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  // Split-K for weight-gradient GEMMs whose output has too few tiles to occupy the SMs (e.g. 768 x 768 x 32768: 36 tiles):
-  // run `splits` K-chunks as a batched GEMM into an fp32 scratch, then sum the chunks in a fixed order (deterministic).
-  if (layout == FSB_GEMM_TN && batch == 1 && bias == nullptr && aux == nullptr && epilogue == FSB_EPI_NONE && M > 0 &&
-      N > 0 && N % 4 == 0 && (M * N) % 8 == 0 && K >= 4096 && (d_dtype == FSB_BF16 || d_dtype == FSB_F32)) {
-    // Preferred: 256 x 256 CTA-pair tiles (a lone 128 x 128 tile is shared-memory-bound at half the MMA rate), K split so
-    // that the SM pairs are busy; small outputs (M or N < 256) keep 128 x 128 tiles.
-    const bool pair = M >= 256 && N >= 256;
-    const int64_t tiles = pair ? ((M + 255) / 256) * ((N + 255) / 256) : ((M + GEMM_BM - 1) / GEMM_BM) * ((N + 127) / 128);
-    const int64_t slots = pair ? num_sms() / 2 : num_sms();
-    int splits = int(slots / tiles);
-    if (splits > 16) splits = 16;
-    while (splits > 1 && (K % (int64_t(splits) * GEMM_BK) != 0 || K / splits < 1024)) --splits;
-    if (splits >= 2 && tiles * 2 <= slots) {
-      float* ws = splitk_workspace(size_t(splits) * M * N * sizeof(float));
-      if (ws == nullptr) { set_error("gemm: cannot allocate the split-K scratch (%zu bytes)", size_t(splits) * M * N * 4); return FSB_ERR_CUDA; }
+  bool pair = false;
+  const int splits = (d_dtype == FSB_BF16 || d_dtype == FSB_F32)
+                         ? splitk_plan(layout, M, N, K, batch, bias == nullptr && aux == nullptr && epilogue == FSB_EPI_NONE, &pair)
+                         : 0;
+  if (splits >= 2) {
+    // the scratch is the caller's (fsb_gemm_workspace_bytes): the library allocates nothing. Too small a workspace is an
+    // error, not a silent change of algorithm (results would still be correct, but run-to-run timing / rounding would not be
+    // what the same call gives with the workspace present).
+    const size_t need = size_t(splits) * size_t(M) * size_t(N) * sizeof(float);
+    FSB_REQUIRE(workspace != nullptr && workspace_bytes >= need && aligned16(workspace),
+                "gemm: this TN call splits K %d ways and needs a %zu-byte workspace (fsb_gemm_workspace_bytes); got %zu",
+                splits, need, workspace_bytes);
+    {
+      float* ws = static_cast<float*>(workspace);
       const int64_t kc = K / splits;
       int rc = gemm_impl(layout, M, N, kc, A, lda, B, ldb, ws, N, FSB_F32, nullptr, FSB_BF16, FSB_EPI_NONE, 0, nullptr, 0,
                          splits, kc * lda, kc * ldb, M * N, 0, stream, pair);

@@ -1,15 +1,23 @@
 """ZeRO-1/2 step engine: what the reference delegates to DeepSpeed through
 `fengshen/strategies/megatron_deepspeed.py:302-320` (`deepspeed.initialize`) and `models/model_utils.py:62-72`
-(`FusedAdam(adam_w_mode=True)`), re-designed for one NVSwitch domain:
+(`FusedAdam(adam_w_mode=True)`), re-designed for one NVSwitch domain.
 
-  backward  : the model reports each bucket (one transformer layer) as soon as its gradients are final; the engine
+  stage 2   : the model reports each bucket (one transformer layer) as soon as its gradients are final; the engine
               reduce-scatters that bucket's bf16 gradients on a side stream (NCCL over NVLink), overlapping the rest of
-              backward. The 1/(world*GA) average is folded into dlogits upstream, so the wire op is a plain SUM.
-  GA        : reduced shards are accumulated into an fp32 shard buffer per micro-step (ZeRO-2 semantics: full-size
-              gradients never outlive a micro-step's bucket).
-  step      : local sum-of-squares of the owned shard -> scalar all-reduce -> clip coefficient (device side, no host
-              sync) -> fused AdamW on the fp32 {master, m, v} shard writing the bf16 parameters of the owned slice in
-              place -> per-bucket in-place all-gather.
+              backward, and accumulates the reduced shard into an fp32 shard buffer when GA > 1. The per-layer buckets
+              share TWO rotating gradient slots (`FlatBuffers.compact_grads`): a full-size gradient buffer never exists
+              ("gradients are partitioned as they are produced"). Slot reuse is fenced with CUDA events: backward may
+              overwrite a slot only after the reduce-scatter that read it has finished.
+  stage 1   : full-size bf16 gradients are kept and accumulated by the wgrad epilogues across the micro-batches; each
+              bucket is reduce-scattered ONCE per optimizer step, during the last micro-batch's backward (1/GA of the
+              stage-2 traffic, +2 B/param of memory): DeepSpeed's "reduce at the gradient-accumulation boundary".
+  step      : (clipping only) local sum-of-squares of the owned shard -> scalar all-reduce -> clip coefficient on the
+              device -> fused AdamW on the fp32 {master, m, v} shard writing the bf16 parameters of the owned slice in
+              place -> per-bucket in-place all-gather ON THE SIDE STREAM, in forward order. The next forward waits per
+              bucket (`model.param_hook`), so the parameter all-gather overlaps the following forward pass instead of
+              sitting exposed at the end of the step. Without clipping, each bucket's AdamW waits only for that bucket's
+              reduce-scatter, so the tail collective overlaps the update of the other buckets.
+The 1/(world*GA) average is folded into dlogits upstream, so the wire op is a plain SUM.
 Sharding is per bucket (fsb200/flat.py): rank r owns slice r of every bucket. With world_size == 1 the same code runs
 with the collectives compiled out of the data path (config 2, single GPU).
 
@@ -22,7 +30,7 @@ import torch.distributed as dist
 
 class ZeroEngine:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1, grad_clip=0.0, ga_steps=1,
-                 process_group=None, stage=2, kernels=None, overlap_comm=True):
+                 process_group=None, stage=2, kernels=None, overlap_comm=True, comm_sms=None):
         self.model = model
         self.flat = model.flat
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -41,23 +49,47 @@ class ZeroEngine:
         dev = self.flat.params.device
         self.device = dev
         n = self.flat.shard_numel
+        nb = len(self.flat.buckets)
         self.master = torch.empty(n, dtype=torch.float32, device=dev)
-        for i in range(len(self.flat.buckets)):
+        for i in range(nb):
             self._seg(self.master, i).copy_(self.flat.bucket_slice(i, self.rank).float())
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.acc32 = torch.zeros(n, dtype=torch.float32, device=dev) if self.ga_steps > 1 else None
+        # stage 2 accumulates reduced shards in fp32 across micro-batches; stage 1 accumulates full bf16 gradients in place
+        self.acc32 = torch.zeros(n, dtype=torch.float32, device=dev) if (self.ga_steps > 1 and self.stage == 2) else None
         self.recv16 = torch.zeros(n, dtype=torch.bfloat16, device=dev) if self.world > 1 else None
         self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self.coef = torch.ones((), dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros((), dtype=torch.float32, device=dev)
         self.use_streams = dev.type == "cuda" and overlap_comm and self.world > 1
         self.comm_stream = torch.cuda.Stream(device=dev) if self.use_streams else None
+        # ZeRO-2: per-layer gradients live in rotating slots whenever they are consumed bucket by bucket (reduced or
+        # accumulated into the fp32 shard); with world == 1 and GA == 1 AdamW reads the full gradients at the step.
+        self.grad_bytes_released = 0
+        if self.stage == 2 and (self.world > 1 or self.acc32 is not None):
+            self.grad_bytes_released = self.flat.compact_grads(slots=2)
+        self.rs_event = [None] * nb      # per bucket: reduce-scatter (+ fp32 accumulation) finished on the side stream
+        self.ag_event = [None] * nb      # per bucket: parameter all-gather finished on the side stream
+        self._last_rot_event = {}        # rotating family -> event of the most recently issued reduce-scatter
         self.micro = 0
         self.step_count = 0
         self.comm_bytes = 0
+        # buckets in the order the forward pass first touches them (no-decay parameters — norms, biases — are read by
+        # every layer, so that bucket is gathered first)
+        order = list(range(nb))
+        nd = [i for i in order if not self.flat.buckets[i][3]]
+        self.fwd_order = nd + [i for i in order if i not in nd]
         model.grad_hook = self._on_bucket
+        model.param_hook = self._need_params
+        model.backward_begin_hook = self._backward_begin
         model.loss_scale = 1.0 / (self.ga_steps * self.world)
+        model.accumulate_grads = False
+        # NCCL's kernels need SMs of their own while they overlap the persistent GEMMs (one CTA per SM, a full register
+        # file each): leave them `comm_sms` SMs instead of letting a GEMM CTA queue behind a collective.
+        # (off by default: measure with bench.py --comm-sms N before turning it on for a config)
+        self.comm_sms = int(comm_sms or 0) if self.use_streams else 0
+        if hasattr(self.k, "set_reserved_sms") and dev.type == "cuda":
+            self.k.set_reserved_sms(self.comm_sms)
 
     # rank-local segment of bucket i inside a shard-sized buffer
     def _seg(self, buf, i):
@@ -65,19 +97,60 @@ class ZeroEngine:
         per = self.flat.buckets[i][2] // self.world
         return buf[off:off + per]
 
+    # ---- forward side ------------------------------------------------------------------------------------------
+    def _need_params(self, name):
+        """The forward pass is about to read bucket `name`: wait for its parameter all-gather (issued by step())."""
+        i = self.flat.bucket_index.get(name)
+        if i is None:
+            return
+        ev = self.ag_event[i]
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self.ag_event[i] = None
+
+    def wait_params(self):
+        """Join every outstanding parameter all-gather (checkpointing, evaluation, reading flat.params from the host)."""
+        for i, ev in enumerate(self.ag_event):
+            if ev is not None:
+                torch.cuda.current_stream(self.device).wait_event(ev)
+                self.ag_event[i] = None
+
     # ---- backward side -----------------------------------------------------------------------------------------
+    def _backward_begin(self):
+        """A micro-batch's backward is about to overwrite gradient buckets: every collective that still reads the
+        previous micro-batch's gradients must have finished (they had a whole forward pass to do so)."""
+        if self.use_streams:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+
+    def _reduce_now(self):
+        return self.stage == 2 or self.micro == self.ga_steps - 1
+
     def _on_bucket(self, name):
         i = self.flat.bucket_index[name]
         first = self.micro == 0
+        if not self._reduce_now():
+            return                      # stage 1: gradients keep accumulating in the full-size bf16 buffer
         if self.world > 1:
             full = self.flat.bucket_view(i, grad=True)
             out = self._seg(self.recv16, i)
             if self.use_streams:
-                self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+                cur = torch.cuda.current_stream(self.device)
+                self.comm_stream.wait_stream(cur)
                 with torch.cuda.stream(self.comm_stream):
                     dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=self.pg)
                     if self.acc32 is not None:
                         self.k.accumulate(self._seg(self.acc32, i), out, 1.0, overwrite=first)
+                    ev = torch.cuda.Event()
+                    ev.record(self.comm_stream)
+                self.rs_event[i] = ev
+                rot = self.flat.rot_group[i]
+                if rot is not None:
+                    # the NEXT layer of this family writes the other slot, last read by the previously issued
+                    # reduce-scatter of the family: backward may proceed into it only once that one is done
+                    prev = self._last_rot_event.get(rot[0])
+                    if prev is not None:
+                        cur.wait_event(prev)
+                    self._last_rot_event[rot[0]] = ev
             else:
                 dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=self.pg)
                 if self.acc32 is not None:
@@ -89,6 +162,9 @@ class ZeroEngine:
     def backward_done(self):
         """Call once after each micro-batch's loss.backward()."""
         self.micro += 1
+        self._last_rot_event.clear()
+        if self.stage == 1:
+            self.model.accumulate_grads = 0 < self.micro < self.ga_steps
 
     def _grad_seg(self, i):
         if self.acc32 is not None:
@@ -97,17 +173,24 @@ class ZeroEngine:
             return self._seg(self.recv16, i)
         return self.flat.bucket_view(i, grad=True)
 
+    def _wait_rs(self, i):
+        ev = self.rs_event[i]
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+            self.rs_event[i] = None
+
     # ---- optimizer step ----------------------------------------------------------------------------------------
     def step(self, lr=None, weight_decay=None):
         if self.micro != self.ga_steps:
             raise RuntimeError(f"ZeroEngine.step() after {self.micro} micro-batches, expected {self.ga_steps}")
         lr = self.lr if lr is None else lr
         wd = self.weight_decay if weight_decay is None else weight_decay
-        if self.use_streams:
-            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
         nb = len(self.flat.buckets)
         coef = None
         if self.grad_clip > 0.0:
+            if self.use_streams:
+                torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+                self.rs_event = [None] * nb
             for i in range(nb):
                 self.k.sumsq(self._grad_seg(i), self.sumsq, accumulate=(i > 0))
             if self.world > 1:
@@ -115,23 +198,48 @@ class ZeroEngine:
             self.k.clip_coef(self.sumsq, self.grad_clip, self.coef, self.grad_norm)
             coef = self.coef
         self.step_count += 1
-        for i in range(nb):
+        cur = torch.cuda.current_stream(self.device) if self.use_streams else None
+        for i in self.fwd_order:
             decay_on = self.flat.buckets[i][3]
+            if self.use_streams:
+                self._wait_rs(i)
             self.k.adamw_flat(self._seg(self.master, i), self._seg(self.exp_avg, i), self._seg(self.exp_avg_sq, i),
                               self._grad_seg(i), self.flat.bucket_slice(i, self.rank), lr, self.betas[0], self.betas[1],
                               self.eps, wd if decay_on else 0.0, self.step_count, coef)
-        if self.world > 1:
-            for i in range(nb):
-                dist.all_gather_into_tensor(self.flat.bucket_view(i), self.flat.bucket_slice(i, self.rank), group=self.pg)
+            if self.world > 1:
+                if self.use_streams:
+                    self.comm_stream.wait_stream(cur)
+                    with torch.cuda.stream(self.comm_stream):
+                        dist.all_gather_into_tensor(self.flat.bucket_view(i), self.flat.bucket_slice(i, self.rank),
+                                                    group=self.pg)
+                        ev = torch.cuda.Event()
+                        ev.record(self.comm_stream)
+                    self.ag_event[i] = ev
+                else:
+                    dist.all_gather_into_tensor(self.flat.bucket_view(i), self.flat.bucket_slice(i, self.rank), group=self.pg)
                 self.comm_bytes += self.flat.buckets[i][2] * 2 * (self.world - 1) // self.world
         self.micro = 0
+        self.model.accumulate_grads = False
+
+    def memory_report(self):
+        """Bytes this engine + the model's flat buffers hold per rank (DESIGN.md §1 memory budget)."""
+        f = self.flat
+        return {"params": f.params.numel() * 2, "grads": f.grads.numel() * f.grads.element_size(),
+                "grads_released_by_zero2": self.grad_bytes_released,
+                "optimizer_state": 3 * self.master.numel() * 4,
+                "acc32": 0 if self.acc32 is None else self.acc32.numel() * 4,
+                "recv16": 0 if self.recv16 is None else self.recv16.numel() * 2}
 
     # ---- checkpoint (rank-local optimizer shard, the analogue of DeepSpeed's zero_pp_rank_*_optim_states.pt) ----
     def state_dict(self):
-        return {"master": self.master, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
-                "step": self.step_count, "world": self.world, "rank": self.rank}
+        self.wait_params()
+        return {"format": "fsb200-zero-shard-v1", "master": self.master, "exp_avg": self.exp_avg,
+                "exp_avg_sq": self.exp_avg_sq, "step": self.step_count, "world": self.world, "rank": self.rank}
 
     def load_state_dict(self, sd):
+        if not isinstance(sd, dict) or "master" not in sd or "world" not in sd:
+            raise ValueError("not an fsb200 optimizer shard (expected keys master / exp_avg / exp_avg_sq / step / world / "
+                             "rank); DeepSpeed's own zero_pp_rank_* files are not readable by this engine")
         if sd["world"] != self.world or sd["rank"] != self.rank:
             raise ValueError("optimizer shard was saved for a different (world, rank)")
         self.master.copy_(sd["master"]); self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])

@@ -68,6 +68,12 @@ class FlatBuffers:
         self.params = torch.zeros(self.total, dtype=torch.bfloat16, device=device)
         self.grads = torch.zeros(self.total, dtype=grad_dtype, device=device)
         self.bucket_index = {b: i for i, (b, _, _, _) in enumerate(self.buckets)}
+        # gradient-space layout: identical to the parameter layout until compact_grads() folds the per-layer buckets
+        # onto rotating slots (ZeRO-2: a full-size gradient buffer never exists)
+        self.grad_bucket_start = [start for _, start, _, _ in self.buckets]
+        self.grad_total = self.total
+        self.rot_group = [None] * len(self.buckets)   # bucket -> (group name, slot) when its gradients live in a rotating slot
+        self._grad_views = []                         # (tensor, parameter-space offset, shape) of every grad view handed out
         # local shard layout: concatenation of this rank's slice of every bucket
         self.shard_offsets, cur = [], 0
         for _, _, length, _ in self.buckets:
@@ -75,10 +81,27 @@ class FlatBuffers:
             cur += length // world_size
         self.shard_numel = cur
 
+    def _bucket_of(self, off):
+        for i, (_, start, length, _) in enumerate(self.buckets):
+            if start <= off < start + length:
+                return i
+        raise ValueError(f"offset {off} outside the flat buffer")
+
+    def _grad_off(self, off):
+        i = self._bucket_of(off)
+        return self.grad_bucket_start[i] + (off - self.buckets[i][1])
+
+    def _grad_view(self, off, shape):
+        g = self._grad_off(off)
+        t = self.grads[g:g + _numel(shape)].view(shape)
+        self._grad_views.append((t, off, tuple(shape)))
+        return t
+
     def view(self, name, grad=False):
         off, shape = self.offsets[name]
-        buf = self.grads if grad else self.params
-        return buf[off:off + _numel(shape)].view(shape)
+        if grad:
+            return self._grad_view(off, shape)
+        return self.params[off:off + _numel(shape)].view(shape)
 
     def span(self, first_name, rows, cols, grad=False):
         """[rows, cols] view starting at `first_name` and covering the adjacent entries after it (fused GEMM operand)."""
@@ -93,17 +116,61 @@ class FlatBuffers:
             cur = o + _numel(shape)
         if covered != rows * cols:
             raise ValueError(f"span({first_name}): {rows}x{cols} does not end on a parameter boundary")
-        buf = self.grads if grad else self.params
-        return buf[off:off + rows * cols].view(rows, cols)
+        if grad:
+            return self._grad_view(off, (rows, cols))
+        return self.params[off:off + rows * cols].view(rows, cols)
 
     def bucket_slice(self, i, rank, grad=False):
         """Rank `rank`'s slice of bucket i inside the flat buffer."""
         _, start, length, _ = self.buckets[i]
         per = length // self.world_size
+        if grad:
+            start = self.grad_bucket_start[i]
         buf = self.grads if grad else self.params
         return buf[start + rank * per: start + (rank + 1) * per]
 
     def bucket_view(self, i, grad=False):
         _, start, length, _ = self.buckets[i]
+        if grad:
+            start = self.grad_bucket_start[i]
         buf = self.grads if grad else self.params
         return buf[start:start + length]
+
+    # ---- ZeRO-2 gradient storage ------------------------------------------------------------------------------------
+    def compact_grads(self, slots=2, min_group=3):
+        """Fold every family of equally sized per-layer buckets (`layer0..layerN`, `enc0..`, `dec0..`) onto `slots` rotating
+        gradient slots: bucket k of a family writes slot k % slots. The engine reduce-scatters a slot before backward reaches
+        the layer that reuses it, so gradients of at most `slots` layers of a family exist at any time — DeepSpeed ZeRO-2's
+        "gradients are partitioned as they are produced"  instead of a full-size buffer. Every grad view
+        handed out so far (prm.main_grad, fused-operand spans) is re-pointed in place. Returns the bytes released."""
+        import re
+        fam = {}
+        for i, (name, _, length, _) in enumerate(self.buckets):
+            m = re.fullmatch(r"(.*?)(\d+)", name)
+            if m:
+                fam.setdefault((m.group(1), length), []).append((int(m.group(2)), i))
+        starts, cur = [None] * len(self.buckets), 0
+        rot = [None] * len(self.buckets)
+        fam_base = {}
+        for i, (name, _, length, _) in enumerate(self.buckets):
+            key = next((k for k, v in fam.items() if any(bi == i for _, bi in v) and len(v) >= min_group), None)
+            if key is None:
+                starts[i] = cur
+                cur += length
+                continue
+            if key not in fam_base:
+                fam_base[key] = cur
+                cur += slots * length
+            k = next(idx for idx, bi in fam[key] if bi == i)
+            rot[i] = (key[0], k % slots)
+            starts[i] = fam_base[key] + (k % slots) * length
+        if not fam_base:
+            return 0
+        new = torch.zeros(cur, dtype=self.grads.dtype, device=self.grads.device)
+        self.grad_bucket_start, self.grad_total, self.rot_group = starts, cur, rot
+        old_bytes = self.grads.numel() * self.grads.element_size()
+        self.grads = new
+        for t, off, shape in self._grad_views:
+            g = self._grad_off(off)
+            t.set_(new.untyped_storage(), g, shape)
+        return old_bytes - cur * new.element_size()

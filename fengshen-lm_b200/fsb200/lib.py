@@ -28,7 +28,9 @@ SIGNATURES = {
     "fsb_num_sms": (c_int, []),
     "fsb_gemm_bf16": (c_int, [c_int, c_i64, c_i64, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int,
                               c_void_p, c_int, c_int, c_int, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64,
-                              c_void_p]),
+                              c_void_p, c_size, c_void_p]),
+    "fsb_gemm_workspace_bytes": (c_size, [c_int, c_i64, c_i64, c_i64]),
+    "fsb_set_reserved_sms": (c_int, [c_int]),
     "fsb_norm_bwd_workspace_bytes": (c_size, [c_i64, c_i64, c_int]),
     "fsb_rmsnorm_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_f32,
                                 c_void_p]),
@@ -56,6 +58,8 @@ SIGNATURES = {
     "fsb_embedding_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64,
                                   c_i64, c_void_p]),
     "fsb_embedding_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
+    "fsb_embedding_bwd_sorted": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_void_p]),
+    "fsb_cast_f32_to_bf16": (c_int, [c_void_p, c_void_p, c_i64, c_void_p]),
     "fsb_softmax_xent_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64,
                                          c_i64, c_i64, c_int, c_int, c_f32, c_void_p]),
     "fsb_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_f32, c_f32, c_f32,
@@ -70,9 +74,11 @@ SIGNATURES = {
     "fsb_scaled_upper_triang_masked_softmax_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_f32, c_void_p]),
     "fsb_softmax_get_batch_per_block": (c_int, [c_i64, c_i64, c_i64, c_i64]),
     "fsb_sdpa_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int,
-                             c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_void_p, c_void_p]),
+                             c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_void_p, c_void_p,
+                             c_void_p]),
+    "fsb_sdpa_bwd_workspace_bytes": (c_size, [c_i64, c_i64, c_i64, c_int]),
     "fsb_sdpa_bwd": (c_int, [c_void_p] * 10 + [c_i64, c_i64, c_i64, c_int, c_int] + [c_i64] * 16 +
-                     [c_f32, c_int, c_void_p, c_void_p]),
+                     [c_f32, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size, c_void_p]),
 }
 
 _lib = None
@@ -111,6 +117,7 @@ def check(rc, what):
 
 kernel_launches = 0  # number of __global__ launches issued by the library on behalf of this process
 # kernels launched per successful entry-point call (everything not listed launches exactly one)
+_NO_KERNEL = {"fsb_set_reserved_sms"}
 _KERNELS_PER_CALL = {"fsb_rmsnorm_bwd": 2, "fsb_layernorm_bwd": 2, "fsb_softmax_xent_fwd_bwd": 3, "fsb_sdpa_bwd": 3,
                      "fsb_sumsq": 2, "fsb_colsum": 2, "fsb_act_bwd_bias": 2}
 
@@ -121,8 +128,9 @@ call_profiler = None  # optional: object with .add(name, ev0, ev1, work); set by
 def call(name, *args, tag=None):
     """Invoke a status-returning entry point and raise on error. `tag` refines the profiler key (e.g. the GEMM shape)."""
     global launch_count, kernel_launches
-    launch_count += 1
-    kernel_launches += _KERNELS_PER_CALL.get(name, 1)
+    if name not in _NO_KERNEL:
+        launch_count += 1
+        kernel_launches += _KERNELS_PER_CALL.get(name, 1)
     if call_profiler is not None:
         import torch
         ev0 = torch.cuda.Event(enable_timing=True); ev0.record()

@@ -183,6 +183,7 @@ class _BertFamily(nn.Module):
         P = self.P
         E = "bert.embeddings."
         scale = 1.0 / math.sqrt(hn)
+        self._need("no_decay"); self._need("emb")
         emb = ops.embedding_fwd(ids, P(E + "word_embeddings.weight").data, pos=pos,
                                 P=P(E + "position_embeddings.weight").data, token_type=tt,
                                 T=P(E + "token_type_embeddings.weight").data, seq_len=S)
@@ -194,6 +195,7 @@ class _BertFamily(nn.Module):
             emb_ctx = (emb, st_e)
         for i in range(self.nl):
             p = f"bert.encoder.layer.{i}."
+            self._need(f"layer{i}")
             if pre:
                 h1, st1, x = ops.layernorm_fwd(x if prev_m is None else prev_m, P(p + "attention.ln.weight").data,
                                                P(p + "attention.ln.bias").data, self.eps,
@@ -225,6 +227,7 @@ class _BertFamily(nn.Module):
                 if save:
                     acts.append((x, qkv, o, lse, x1, st2, h2, prea, f, s2, st3))
                 x = xo
+        self._need("head")
         if pre:
             hf, stf, xf = ops.layernorm_fwd(prev_m, P("bert.encoder.ln.weight").data, P("bert.encoder.ln.bias").data,
                                             self.eps, residual=x)
@@ -271,6 +274,7 @@ class _BertFamily(nn.Module):
         T = B * S
         P = self.P
         acc = self.accumulate_grads
+        self._begin_backward()
         E = "bert.embeddings."
         scale = 1.0 / math.sqrt(hn)
         if gloss is not None:
@@ -395,6 +399,17 @@ class _BertFamily(nn.Module):
     def _done(self, bucket):
         if self.grad_hook is not None:
             self.grad_hook(bucket)
+
+    def _need(self, bucket):
+        """Forward is about to read this bucket's parameters (the engine may still be all-gathering them)."""
+        hook = getattr(self, "param_hook", None)
+        if hook is not None:
+            hook(bucket)
+
+    def _begin_backward(self):
+        hook = getattr(self, "backward_begin_hook", None)
+        if hook is not None:
+            hook()
 
 
 class BertForMaskedLM(_BertFamily):

@@ -143,10 +143,12 @@ class GPT2LMHeadModel(nn.Module):
         h, nh, hn = self.h, self.nh, self.hn
         T = B * S
         tr = self.transformer
+        self._need("no_decay"); self._need("wte")
         x = ops.embedding_fwd(ids, tr.wte.weight.data, pos=pos, P=tr.wpe.weight.data, seq_len=S)
         acts, prev_m = [], None
         scale = 1.0 / math.sqrt(hn)
-        for blk in tr.h:
+        for i, blk in enumerate(tr.h):
+            self._need(f"layer{i}")
             h1, st1, x = ops.layernorm_fwd(x if prev_m is None else prev_m, blk.ln_1.weight.data, blk.ln_1.bias.data,
                                            self.eps, residual=None if prev_m is None else x)
             qkv = ops.gemm(L.GEMM_NN, h1, blk.attn.c_attn.weight.data, bias=blk.attn.c_attn.bias.data)
@@ -179,6 +181,7 @@ class GPT2LMHeadModel(nn.Module):
         h, nh, hn = self.h, self.nh, self.hn
         T = B * S
         acc = self.accumulate_grads
+        self._begin_backward()
         tr = self.transformer
         scale = 1.0 / math.sqrt(hn)
         if gloss is not None:
@@ -235,6 +238,17 @@ class GPT2LMHeadModel(nn.Module):
     def _done(self, bucket):
         if self.grad_hook is not None:
             self.grad_hook(bucket)
+
+    def _need(self, bucket):
+        """Forward is about to read this bucket's parameters (the engine may still be all-gathering them)."""
+        hook = getattr(self, "param_hook", None)
+        if hook is not None:
+            hook(bucket)
+
+    def _begin_backward(self):
+        hook = getattr(self, "backward_begin_hook", None)
+        if hook is not None:
+            hook()
 
 
 class _GPT2Step(torch.autograd.Function):

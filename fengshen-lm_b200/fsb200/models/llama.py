@@ -115,16 +115,26 @@ class LlamaForCausalLM(nn.Module):
         self._dw13 = [self.flat.span(f"llama.layers.{i}.mlp.w1.weight", 2 * self.ff, h, grad=True) for i in range(nl)]
 
         # RoPE tables exactly as RotaryEmbedding builds them (layers/positional_embeddings.py:38-52), fp32
-        max_pos = getattr(config, "max_position_embeddings", 2048)
-        t = torch.arange(max_pos, dtype=inv_freq.dtype)
-        freqs = torch.einsum("i,j->ij", t, inv_freq)
-        self.register_buffer("_cos", freqs.cos().contiguous().to(dev), persistent=False)
-        self.register_buffer("_sin", freqs.sin().contiguous().to(dev), persistent=False)
+        self._inv_freq = inv_freq
+        self._rope_rows = 0
+        self._ensure_rope(getattr(config, "max_position_embeddings", 2048), dev)
 
         self.reset_parameters(seed)
         self.accumulate_grads = False   # set by the engine for micro-batches after the first
         self.loss_scale = 1.0           # 1 / (gradient_accumulation_steps * world_size), folded into dlogits
         self.grad_hook = None           # engine callback: grad_hook(bucket_name) when a bucket's gradients are final
+
+    def _ensure_rope(self, n, dev=None):
+        """cos/sin tables with at least n rows. RotaryEmbedding regrows its cache when a longer sequence arrives
+        (positional_embeddings.py:54-68); fsb_rope_inplace never reads past the table (rows beyond it become NaN)."""
+        if n <= self._rope_rows:
+            return
+        dev = dev if dev is not None else self.flat.params.device
+        t = torch.arange(n, dtype=self._inv_freq.dtype)
+        freqs = torch.einsum("i,j->ij", t, self._inv_freq)
+        self._cos = freqs.cos().contiguous().to(dev)
+        self._sin = freqs.sin().contiguous().to(dev)
+        self._rope_rows = n
 
     # ---- init (layers/init_functions.py:121-142: small_init std sqrt(2/(5h)); wang_init std 2/(L*sqrt(h))) -------------
     @torch.no_grad()
@@ -179,9 +189,20 @@ class LlamaForCausalLM(nn.Module):
         dev = self.flat.params.device
         ids = input_ids.to(device=dev, dtype=torch.int64).contiguous().view(-1)
         if position_ids is None:
+            self._ensure_rope(S)
             pos = torch.arange(S, device=dev, dtype=torch.int64).repeat(B)
         else:
+            if not position_ids.is_cuda:   # host tensor (the collators emit CPU batches): exact bound, no device sync
+                lo, hi = int(position_ids.min()), int(position_ids.max())
+                if lo < 0:
+                    raise ValueError(f"position_ids must be non-negative, got {lo}")
+                self._ensure_rope(hi + 1)
             pos = position_ids.to(device=dev, dtype=torch.int64).expand(B, S).contiguous().view(-1)
+            if position_ids.is_cuda:       # device tensor: asynchronous device-side check against the table size
+                self._ensure_rope(S)
+                torch._assert_async(((pos >= 0) & (pos < self._rope_rows)).all(),
+                                    "fsb200 LlamaForCausalLM: position_ids outside [0, rope table rows); pass them on the "
+                                    "host or raise config.max_position_embeddings")
         lab = None if labels is None else labels.to(device=dev, dtype=torch.int64).contiguous().view(-1)
         if lab is not None and torch.is_grad_enabled():
             # a leaf that requires grad makes the node differentiable; real gradients go to the flat grad buffer
@@ -196,9 +217,11 @@ class LlamaForCausalLM(nn.Module):
         h, nh, hn, ff = self.h, self.nh, self.hn, self.ff
         T = B * S
         acts = []
+        self._need("no_decay"); self._need("embed_in")
         x = ops.embedding_fwd(ids, self.llama.embed_in.word_embeddings.weight.data)
         prev_m = None
         for i, lyr in enumerate(self.llama.layers):
+            self._need(f"layer{i}")
             h1, rstd1, x = ops.rmsnorm_fwd(x if prev_m is None else prev_m, lyr.input_layernorm.scale.data, self.eps,
                                            residual=None if prev_m is None else x)
             qkv = ops.gemm(L.GEMM_NT, h1, lyr.attention.query_key_value.weight.data)
@@ -215,6 +238,7 @@ class LlamaForCausalLM(nn.Module):
             if save:
                 acts.append((x, rstd1, h1, qkv, o, lse, x1, rstd2, h2, gu, act))
             x, prev_m = x1, m
+        self._need("head")
         hf, rstdf, xf = ops.rmsnorm_fwd(prev_m, self.llama.final_layer_norm.scale.data, self.eps, residual=x)
         logits = ops.gemm(L.GEMM_NT, hf, self.embed_out.final_linear.weight.data)
         loss = None
@@ -234,6 +258,7 @@ class LlamaForCausalLM(nn.Module):
         h, nh, hn, ff = self.h, self.nh, self.hn, self.ff
         T = B * S
         acc = self.accumulate_grads
+        self._begin_backward()
         if gloss is not None:
             ops.scale_inplace(dlogits, gloss)  # upstream scalar; the kernel exits immediately when it is 1.0
         W_out = self.embed_out.final_linear.weight
@@ -283,6 +308,17 @@ class LlamaForCausalLM(nn.Module):
     def _done(self, bucket):
         if self.grad_hook is not None:
             self.grad_hook(bucket)
+
+    def _need(self, bucket):
+        """Forward is about to read this bucket's parameters (the engine may still be all-gathering them)."""
+        hook = getattr(self, "param_hook", None)
+        if hook is not None:
+            hook(bucket)
+
+    def _begin_backward(self):
+        hook = getattr(self, "backward_begin_hook", None)
+        if hook is not None:
+            hook()
 
 
 class _LlamaStep(torch.autograd.Function):

@@ -75,12 +75,20 @@ def gemm(layout, a, b, out=None, out_dtype=_bf16, bias=None, epilogue=L.EPI_NONE
     if aux is not None:
         _chk(aux, _bf16, "aux")
         _, _, ldaux = _rows2d(aux, "aux")
+    ws, ws_bytes = None, 0
+    if layout == L.GEMM_TN and bias is None and aux is None and epilogue == L.EPI_NONE:
+        key = (M, N, K)
+        ws_bytes = _splitk_bytes.get(key)
+        if ws_bytes is None:
+            ws_bytes = _splitk_bytes[key] = int(L.load().fsb_gemm_workspace_bytes(layout, M, N, K))
+        if ws_bytes:
+            ws = workspace(ws_bytes, a.device, "gemm_splitk")   # one stream issues the step's GEMMs: a shared scratch is safe
     prof = _profiler
     if prof is not None:
         ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
     L.call("fsb_gemm_bf16", layout, M, N, K, _p(a), lda, _p(b), ldb, _p(out), ldd,
            L.F32 if out.dtype == torch.float32 else L.BF16, _p(bias), bias_dt, epilogue, int(bool(accumulate)),
-           _p(aux), ldaux, 1, 0, 0, 0, 0, _stream(),
+           _p(aux), ldaux, 1, 0, 0, 0, 0, _p(ws), ws_bytes, _stream(),
            tag=(f"{('NT', 'NN', 'TN')[layout]} {M}x{N}x{K} epi{epilogue} acc{int(bool(accumulate))} "
                 f"{'f32' if out.dtype == torch.float32 else 'bf16'}{' bias' if bias is not None else ''}"
                 f"{' aux' if aux is not None else ''}") if L.call_profiler is not None else None)
@@ -88,6 +96,14 @@ def gemm(layout, a, b, out=None, out_dtype=_bf16, bias=None, epilogue=L.EPI_NONE
         ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
         prof.add("gemm_bf16_kernel", ev0, ev1, 2.0 * M * N * K)
     return out
+
+
+_splitk_bytes = {}
+
+
+def set_reserved_sms(n):
+    """Leave n SMs (2n for CTA-pair kernels) of every persistent GEMM grid to overlapping communication kernels."""
+    L.call("fsb_set_reserved_sms", int(n))
 
 
 class KernelProfiler:
@@ -250,8 +266,21 @@ def embedding_fwd(ids, W, pos=None, P=None, token_type=None, T=None, seq_len=1):
 
 
 def embedding_bwd(ids, dout, dW, idx_mod=0):
+    """dW[ids[t]] += dout[t]. With ids: deterministic — the ids are sorted (torch.sort: integer index plumbing) and every
+    distinct row is summed in fp32 in a fixed order, one bf16 rounding. ids=None: row t % idx_mod (bf16 atomics)."""
     rows, cols = dout.shape
-    L.call("fsb_embedding_bwd", _p(ids), _p(dout), _p(dW), rows, cols, idx_mod, _stream())
+    if ids is None:
+        L.call("fsb_embedding_bwd", None, _p(dout), _p(dW), rows, cols, idx_mod, _stream())
+        return
+    ids_sorted, order = torch.sort(ids.view(-1), stable=True)
+    L.call("fsb_embedding_bwd_sorted", _p(ids_sorted), _p(order), _p(dout), _p(dW), rows, cols, _stream())
+
+
+def cast_f32_to_bf16(x32, out=None):
+    if out is None:
+        out = torch.empty(x32.shape, dtype=_bf16, device=x32.device)
+    L.call("fsb_cast_f32_to_bf16", _p(x32), _p(out), x32.numel(), _stream())
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------ loss / optim
@@ -300,8 +329,16 @@ def _bshd(t, name):
     return B, S, H, D, t.stride(1), t.stride(2)
 
 
-def sdpa_fwd(q, k, v, scale, causal, kv_mask=None, out=None):
-    """q,k,v: strided [B,S,H,D] bf16 views (e.g. slices of the packed QKV projection). Returns (out [B,Sq,H,D], lse)."""
+def _chk_rel(rel, H, Sq, Skv, name):
+    _chk(rel, torch.float32, name)
+    if tuple(rel.shape) != (H, Sq + Skv - 1) or not rel.is_contiguous():
+        raise RuntimeError(f"fsb200: {name} must be contiguous fp32 [heads, seq_q + seq_kv - 1] = [{H}, {Sq + Skv - 1}], "
+                           f"got {tuple(rel.shape)}")
+
+
+def sdpa_fwd(q, k, v, scale, causal, kv_mask=None, out=None, rel_bias=None):
+    """q,k,v: strided [B,S,H,D] bf16 views (e.g. slices of the packed QKV projection). Returns (out [B,Sq,H,D], lse).
+    rel_bias: optional fp32 [H, Sq + Skv - 1] additive bias over the offset k - q (T5 relative-position bias)."""
     _chk(q, _bf16, "q"); _chk(k, _bf16, "k"); _chk(v, _bf16, "v")
     B, Sq, H, D, q_rs, q_hs = _bshd(q, "q")
     _, Skv, _, _, k_rs, k_hs = _bshd(k, "k")
@@ -314,13 +351,16 @@ def sdpa_fwd(q, k, v, scale, causal, kv_mask=None, out=None):
         _chk(kv_mask, torch.uint8, "kv_mask")
         if tuple(kv_mask.shape) != (B, Skv) or not kv_mask.is_contiguous():
             raise RuntimeError("fsb200: kv_mask must be contiguous uint8 [batch, seq_kv]")
+    if rel_bias is not None:
+        _chk_rel(rel_bias, H, Sq, Skv, "rel_bias")
     L.call("fsb_sdpa_fwd", _p(q), _p(k), _p(v), _p(out), _p(lse), B, Sq, Skv, H, D, q_rs, k_rs, v_rs, o_rs, q_hs, k_hs,
-           v_hs, o_hs, float(scale), int(bool(causal)), _p(kv_mask), _stream())
+           v_hs, o_hs, float(scale), int(bool(causal)), _p(kv_mask), _p(rel_bias), _stream())
     return out, lse
 
 
-def sdpa_bwd(q, k, v, out, dout, lse, scale, causal, dq, dk, dv, kv_mask=None):
-    """All tensors strided [B,S,H,D] bf16 views; dq/dk/dv are written (e.g. slices of a packed dQKV buffer)."""
+def sdpa_bwd(q, k, v, out, dout, lse, scale, causal, dq, dk, dv, kv_mask=None, rel_bias=None, drel_bias=None):
+    """All tensors strided [B,S,H,D] bf16 views; dq/dk/dv are written (e.g. slices of a packed dQKV buffer).
+    rel_bias as in sdpa_fwd; drel_bias (fp32 [H, Sq + Skv - 1]) is accumulated into (+=), deterministically."""
     B, Sq, H, D, q_rs, q_hs = _bshd(q, "q")
     _, Skv, _, _, k_rs, k_hs = _bshd(k, "k")
     _, _, _, _, v_rs, v_hs = _bshd(v, "v")
@@ -332,6 +372,13 @@ def sdpa_bwd(q, k, v, out, dout, lse, scale, causal, dq, dk, dv, kv_mask=None):
     for t, n in ((dout, "dout"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
         _chk(t, _bf16, n)
     delta = torch.empty((B, H, Sq), dtype=torch.float32, device=q.device)
+    ws, ws_bytes = None, 0
+    if rel_bias is not None:
+        _chk_rel(rel_bias, H, Sq, Skv, "rel_bias")
+    if drel_bias is not None:
+        _chk_rel(drel_bias, H, Sq, Skv, "drel_bias")
+        ws_bytes = int(L.load().fsb_sdpa_bwd_workspace_bytes(B, Sq, Skv, H))
+        ws = workspace(ws_bytes, q.device, "sdpa_dbias")
     L.call("fsb_sdpa_bwd", _p(q), _p(k), _p(v), _p(out), _p(dout), _p(lse), _p(delta), _p(dq), _p(dk), _p(dv), B, Sq, Skv,
            H, D, q_rs, k_rs, v_rs, o_rs, do_rs, dq_rs, dk_rs, dv_rs, q_hs, k_hs, v_hs, o_hs, do_hs, dq_hs, dk_hs, dv_hs,
-           float(scale), int(bool(causal)), _p(kv_mask), _stream())
+           float(scale), int(bool(causal)), _p(kv_mask), _p(rel_bias), _p(drel_bias), _p(ws), ws_bytes, _stream())

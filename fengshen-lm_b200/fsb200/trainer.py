@@ -13,10 +13,10 @@ from .engine import ZeroEngine
 
 class PretrainStep:
     def __init__(self, model, lr_fn, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1, grad_clip=0.0, ga_steps=1,
-                 process_group=None, stage=2):
+                 process_group=None, stage=2, comm_sms=0):
         self.model = model
         self.engine = ZeroEngine(model, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, grad_clip=grad_clip,
-                                 ga_steps=ga_steps, process_group=process_group, stage=stage)
+                                 ga_steps=ga_steps, process_group=process_group, stage=stage, comm_sms=comm_sms)
         self.lr_fn = lr_fn
         self.global_step = 0
         self.device = model.flat.params.device

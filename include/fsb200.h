@@ -6,7 +6,8 @@
  * extensions (flash_attn_cuda, deepspeed.ops.adam.FusedAdam, cuBLAS via F.linear). Every entry below names the
  * reference call site it replaces. Conventions:
  *   - plain pointers + sizes only; all pointers are DEVICE pointers unless stated; caller owns every buffer;
- *   - the library never allocates device memory and never synchronises: work is enqueued on `stream`;
+ *   - the library never allocates device memory and never synchronises: work is enqueued on `stream`; every scratch
+ *     buffer is a caller-owned `workspace` whose size a fsb_*_workspace_bytes() query returns;
  *   - row-major tensors; "ld*" are row strides in ELEMENTS;
  *   - bf16 activations/weights, fp32 statistics / optimizer state;
  *   - return 0 on success, negative fsb_status on error; fsb_last_error() gives a thread-local message;
@@ -58,8 +59,11 @@ int fsb_num_sms(void);               /* SM count of the current device (148 on B
  * `batch` > 1 runs independent GEMMs with element strides stride_a/b/d between them (use 1 and 0 otherwise).
  * Kernel selection is internal: CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles) when the output has at least one such tile
  * per SM pair, single-CTA 128 x 256 / 128 x 128 tiles otherwise. FSB_GEMM_TN calls whose output has few tiles and K >= 4096
- * (weight gradients of small models) split K: the chunks are accumulated in fp32 in a per-device scratch the library grows on
- * first use and reduced in a fixed order (results are deterministic); such calls must not run concurrently on several streams.
+ * (weight gradients of small models) split K: the chunks are accumulated in fp32 in the caller's `workspace`
+ * (fsb_gemm_workspace_bytes(layout, M, N, K) bytes; 0 when the call does not split) and reduced in a fixed order — results
+ * are deterministic; a split call with too small a workspace is an error. Other calls ignore `workspace` (may be NULL).
+ * fsb_set_reserved_sms(n): persistent GEMM grids leave n SMs (2n for CTA-pair kernels) to communication kernels that
+ * overlap them (the ZeRO engine's reduce-scatter / all-gather on the side stream); 0 restores the full grid.
  * FSB_EPI_GELU_ERF evaluates erf through Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, below the bf16 rounding of the output).
  */
 typedef enum { FSB_GEMM_NT = 0, FSB_GEMM_NN = 1, FSB_GEMM_TN = 2 } fsb_gemm_layout;
@@ -75,7 +79,9 @@ int fsb_gemm_bf16(int layout, int64_t M, int64_t N, int64_t K,
                   const void* bias, int bias_dtype, int epilogue, int accumulate,
                   void* aux, int64_t ldaux,
                   int64_t batch, int64_t stride_a, int64_t stride_b, int64_t stride_d, int64_t stride_aux,
-                  fsb_stream_t stream);
+                  void* workspace, size_t workspace_bytes, fsb_stream_t stream);
+size_t fsb_gemm_workspace_bytes(int layout, int64_t M, int64_t N, int64_t K);
+int fsb_set_reserved_sms(int n);
 
 /* ---- RMSNorm / LayerNorm ------------------------------------------------------------------------------------
  * RMSNorm.forward fengshen/models/megatron/layers/norms.py:44-52 (y = scale * cast(x * rsqrt(mean(x^2) + eps)), the cast to
@@ -101,7 +107,9 @@ int fsb_layernorm_bwd(const void* dy, const void* x, const void* gamma, const fl
  * apply_rotary_pos_emb / rotate_half, layers/positional_embeddings.py:71-87, applied to one of {q, k} inside the packed QKV
  * projection output (layers/transformer.py:488-523): head h of row t starts at x + t*row_stride + h*head_stride.
  * cos/sin: fp32 [max_pos, head_dim/2] (RotaryEmbedding cache, positional_embeddings.py:38-52); positions int64 [rows].
- * backward != 0 applies the transposed rotation (gradient). head_dim % 16 == 0. */
+ * backward != 0 applies the transposed rotation (gradient). head_dim % 16 == 0. A position outside [0, max_pos) never
+ * reads outside the tables: its row is filled with NaN (the reference regrows the cache instead, :54-68 — the host
+ * wrapper sizes the tables to the sequence and validates position_ids). */
 int fsb_rope_inplace(void* x, const float* cos_table, const float* sin_table, const int64_t* positions, int64_t rows,
                      int nheads, int head_dim, int64_t row_stride, int64_t head_stride, int64_t max_pos, int backward,
                      fsb_stream_t stream);
@@ -136,11 +144,18 @@ int fsb_colsum(const void* x, int64_t rows, int64_t cols, int64_t ld, void* out,
 /* ---- embedding ----------------------------------------------------------------------------------------------
  * VocabParallelEmbedding.forward fengshen/models/megatron/mpu/layers.py:104-130 (TP = 1): out[t] = W[ids[t]]
  * (+ P[pos[t]] learned positions, pos == NULL -> t % seq_len; + T[token_type[t]]) — HF BertEmbeddings / GPT-2 wte + wpe.
- * Backward scatter-adds bf16 rows into dW (ids == NULL -> row t % idx_mod). */
+ * Backward: fsb_embedding_bwd_sorted is the deterministic form — `ids_sorted` (ascending, stable) and `order` (token index of
+ * each sorted position) come from a sort of the ids; every distinct id's rows are summed in fp32 in a fixed order and added
+ * onto dW[id] with ONE bf16 rounding (torch's embedding backward, which the reference runs, accumulates in fp32 too).
+ * fsb_embedding_bwd scatter-adds with bf16x2 atomics (kept for ids == NULL -> row t % idx_mod, learned positions).
+ * fsb_cast_f32_to_bf16: out = bf16(in), n % 8 == 0 (fp32 gradient accumulators handed back to bf16 kernels). */
 int fsb_embedding_fwd(const int64_t* ids, const int64_t* pos, const int64_t* token_type, const void* W, const void* P,
                       const void* T, void* out, int64_t rows, int64_t cols, int64_t seq_len, fsb_stream_t stream);
 int fsb_embedding_bwd(const int64_t* ids, const void* dout, void* dW, int64_t rows, int64_t cols, int64_t idx_mod,
                       fsb_stream_t stream);
+int fsb_embedding_bwd_sorted(const int64_t* ids_sorted, const int64_t* order, const void* dout, void* dW, int64_t rows,
+                             int64_t cols, fsb_stream_t stream);
+int fsb_cast_f32_to_bf16(const float* in, void* out, int64_t n, fsb_stream_t stream);
 
 /* ---- fused softmax cross-entropy, forward + backward ----------------------------------------------------------
  * torch.nn.CrossEntropyLoss()(shift_logits, shift_labels), fengshen/models/llama/modeling_llama.py:334-339: mean NLL over
@@ -193,15 +208,25 @@ int fsb_softmax_get_batch_per_block(int64_t sq, int64_t sk, int64_t batches, int
  * o: same addressing with o_*_stride. lse: fp32 [batch, nheads, seq_q], log2 domain (internal, consumed by bwd).
  * kv_mask: optional uint8 [batch, seq_kv], 1 = attend (HF additive padding mask), NULL = none.
  * causal=1 masks key > query (requires seq_q == seq_kv). head_dim in {64, 128}.
+ * rel_bias: optional fp32 [nheads, seq_q + seq_kv - 1], natural-log units, added to scale * q.k before the softmax:
+ *   bias(h, q, k) = rel_bias[h][k - q + seq_q - 1]  — the T5 / mT5 relative-position bias (transformers
+ *   mt5/modeling_mt5.py:181-235,:320: an embedding over bucket(k - q), shared by every layer of a stack), used by
+ *   fengshen/examples/pretrain_t5/pretrain_t5.py:57-59 (scale = 1: T5 attention is unscaled, :300). NULL = none.
  */
 int fsb_sdpa_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
                  int64_t batch, int64_t seq_q, int64_t seq_kv, int nheads, int head_dim,
                  int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride,
                  int64_t q_head_stride, int64_t k_head_stride, int64_t v_head_stride, int64_t o_head_stride,
-                 float scale, int causal, const uint8_t* kv_mask, fsb_stream_t stream);
+                 float scale, int causal, const uint8_t* kv_mask, const float* rel_bias, fsb_stream_t stream);
 
 /* Backward of fsb_sdpa_fwd. o/lse are the forward outputs; delta: fp32 scratch [batch, nheads, seq_q] (written here);
- * dq/dk/dv are written with their own strides (e.g. the three slices of a packed dQKV buffer). Deterministic. */
+ * dq/dk/dv are written with their own strides (e.g. the three slices of a packed dQKV buffer). Deterministic.
+ * rel_bias as in the forward; drel_bias (fp32 [nheads, seq_q + seq_kv - 1], may be NULL) is ACCUMULATED into:
+ *   drel_bias[h][r] += sum over (batch, q) of dS[q, q + r - (seq_q - 1)]   (gradient w.r.t. the bias vector; the
+ * [buckets, heads] table gradient is its scatter over bucket(r), autograd of T5Attention.compute_bias). It needs a workspace of
+ * fsb_sdpa_bwd_workspace_bytes(batch, seq_q, seq_kv, nheads) bytes: per-warp diagonal sums written by the dQ kernel and
+ * reduced in a fixed order (no atomics). */
+size_t fsb_sdpa_bwd_workspace_bytes(int64_t batch, int64_t seq_q, int64_t seq_kv, int nheads);
 int fsb_sdpa_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
                  const float* lse, float* delta, void* dq, void* dk, void* dv,
                  int64_t batch, int64_t seq_q, int64_t seq_kv, int nheads, int head_dim,
@@ -209,7 +234,8 @@ int fsb_sdpa_bwd(const void* q, const void* k, const void* v, const void* o, con
                  int64_t do_row_stride, int64_t dq_row_stride, int64_t dk_row_stride, int64_t dv_row_stride,
                  int64_t q_head_stride, int64_t k_head_stride, int64_t v_head_stride, int64_t o_head_stride,
                  int64_t do_head_stride, int64_t dq_head_stride, int64_t dk_head_stride, int64_t dv_head_stride,
-                 float scale, int causal, const uint8_t* kv_mask, fsb_stream_t stream);
+                 float scale, int causal, const uint8_t* kv_mask, const float* rel_bias, float* drel_bias,
+                 void* workspace, size_t workspace_bytes, fsb_stream_t stream);
 
 #ifdef __cplusplus
 }

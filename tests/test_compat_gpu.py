@@ -42,3 +42,36 @@ def test_example_script_trains_checkpoints_and_resumes(tmp_path):
     assert trainer2.global_step == 16
     assert getattr(module2, "consumed_samples", None) == 48          # on_load_checkpoint hook (finetune_ziya_llama.py:180-183)
     assert not torch.equal(module2.model.flat.params, w_before)
+
+
+def test_resumed_run_continues_the_sample_stream(tmp_path, monkeypatch):
+    """the loader built for get_total_steps() (before the checkpoint is read) must not survive the resume —
+    the first batch of a resumed run is the one that follows the last consumed sample of the permutation
+    (PretrainingRandomSampler, universal_sampler.py:104-125), not sample 0 again."""
+    import pretrain_ziya_llama as ex
+    seen = []
+    orig = ex.SyntheticCollator.__call__
+
+    def spy(self, samples):
+        out = orig(self, samples)
+        seen.append(out["input_ids"][:, :4].clone())
+        return out
+    monkeypatch.setattr(ex.SyntheticCollator, "__call__", spy)
+    common = ("--replace_sampler_ddp", "False", "--num_samples", "64", "--every_n_train_steps", "4")
+    straight = tmp_path / "a"; straight.mkdir()
+    ex.main(_args(straight, common + ("--max_steps", "8")))
+    want = [t.clone() for t in seen]
+    seen.clear()
+    resumed = tmp_path / "b"; resumed.mkdir()
+    ex.main(_args(resumed, common + ("--max_steps", "4")))
+    first_leg = len(seen)
+    trainer2, module2 = ex.main(_args(resumed, common + ("--max_steps", "8")))
+    assert trainer2.global_step == 8 and module2.consumed_samples == 16
+    got = seen[:4] + seen[first_leg:first_leg + 4] if first_leg >= 4 else seen
+    # the 4 batches consumed after the resume are batches 5..8 of the uninterrupted run
+    resumed_batches = seen[first_leg:]
+    assert len(resumed_batches) >= 4
+    for a, b in zip(resumed_batches[:4], want[4:8]):
+        assert torch.equal(a, b), "resumed run replayed already-consumed samples"
+    # and the first resumed step used the restored learning rate, not the schedule's step-0 value
+    assert trainer2.optimizers[0].param_groups[0]["lr"] > 0

@@ -77,14 +77,24 @@ class _ToyModel:
     def fake_backward(self, rank, micro):
         """Deterministic per-(rank, micro) gradients, reported bucket by bucket in backward order."""
         g = torch.Generator().manual_seed(1000 + 10 * rank + micro)
-        for name in self.flat.offsets:
-            grad = torch.randn(self.flat.offsets[name][1], generator=g) * self.loss_scale
-            self.flat.view(name, grad=True).copy_(grad.to(torch.bfloat16))
+        grads = {name: torch.randn(self.flat.offsets[name][1], generator=g) * self.loss_scale for name in self.flat.offsets}
+        if getattr(self, "backward_begin_hook", None):
+            self.backward_begin_hook()
+        # a layer's gradients are written, THEN its bucket is reported — layer buckets may share rotating slots (ZeRO-2)
         for b in ["head", "layer2", "layer1", "layer0", "emb", "no_decay"]:
+            i = self.flat.bucket_index[b]
+            _, start, length, _ = self.flat.buckets[i]
+            for name, (off, _) in self.flat.offsets.items():
+                if start <= off < start + length:
+                    gv = self.flat.view(name, grad=True)
+                    if getattr(self, "accumulate_grads", False):
+                        gv.copy_((gv.float() + grads[name].to(torch.bfloat16).float()).to(torch.bfloat16))
+                    else:
+                        gv.copy_(grads[name].to(torch.bfloat16))
             self.grad_hook(b)
 
 
-def _reference(world, ga, steps, lr, wd, clip):
+def _reference(world, ga, steps, lr, wd, clip, stage=2):
     """Single process: fp32 master AdamW over the sum of every rank's (already 1/(world*ga)-scaled, bf16) gradients."""
     import cpu_kernels as K
     ref = _ToyModel(1)
@@ -94,19 +104,32 @@ def _reference(world, ga, steps, lr, wd, clip):
     scale = 1.0 / (world * ga)
     for step in range(1, steps + 1):
         total = torch.zeros_like(master)
-        for micro in range(ga):
-            # bf16 wire reduction of the ranks' bucket gradients, then fp32 accumulation over micro-steps
+
+        def rank_grads(r, micro):
+            g = torch.Generator().manual_seed(1000 + 10 * r + micro)
+            tmp = torch.zeros(fb.total, dtype=torch.bfloat16)
+            for name, (off, shape) in fb.offsets.items():
+                n = 1
+                for s in shape:
+                    n *= s
+                tmp[off:off + n] = (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).flatten()
+            return tmp
+        if stage == 2:
+            for micro in range(ga):
+                # bf16 wire reduction of the ranks' bucket gradients, then fp32 accumulation over micro-steps
+                wire = torch.zeros(fb.total, dtype=torch.bfloat16)
+                for r in range(world):
+                    wire = (wire.float() + rank_grads(r, micro).float()).to(torch.bfloat16)
+                total += wire.float()
+        else:
+            # stage 1: every rank accumulates its micro-batches in bf16, ONE bf16 wire reduction at the GA boundary
             wire = torch.zeros(fb.total, dtype=torch.bfloat16)
             for r in range(world):
-                g = torch.Generator().manual_seed(1000 + 10 * r + micro)
-                tmp = torch.zeros(fb.total, dtype=torch.bfloat16)
-                for name, (off, shape) in fb.offsets.items():
-                    n = 1
-                    for s in shape:
-                        n *= s
-                    tmp[off:off + n] = (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).flatten()
-                wire = (wire.float() + tmp.float()).to(torch.bfloat16)
-            total += wire.float()
+                acc = torch.zeros(fb.total, dtype=torch.bfloat16)
+                for micro in range(ga):
+                    acc = (acc.float() + rank_grads(r, micro).float()).to(torch.bfloat16)
+                wire = (wire.float() + acc.float()).to(torch.bfloat16)
+            total = wire.float()
         coef = None
         if clip > 0:
             nrm = total.pow(2).sum().sqrt()
@@ -117,14 +140,18 @@ def _reference(world, ga, steps, lr, wd, clip):
     return master.to(torch.bfloat16)
 
 
-def _worker(rank, world, ga, steps, clip, port, q):
+def _worker(rank, world, ga, steps, clip, port, q, stage=2):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import cpu_kernels as K
     from fsb200.engine import ZeroEngine
     model = _ToyModel(world)
     eng = ZeroEngine(model, lr=1e-2, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1, grad_clip=clip, ga_steps=ga,
-                     kernels=K, overlap_comm=False)
+                     kernels=K, overlap_comm=False, stage=stage)
+    if stage == 2:   # per-layer gradient buckets share two rotating slots: no full-size gradient buffer
+        assert model.flat.grads.numel() < model.flat.total and eng.grad_bytes_released > 0
+    else:
+        assert model.flat.grads.numel() == model.flat.total
     assert model.loss_scale == 1.0 / (world * ga)
     for _ in range(steps):
         for micro in range(ga):
@@ -136,13 +163,13 @@ def _worker(rank, world, ga, steps, clip, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ga,clip", [(1, 0.0), (2, 1.0)])
-def test_zero_engine_world2_gloo_matches_single_process_adamw(ga, clip):
+@pytest.mark.parametrize("ga,clip,stage", [(1, 0.0, 2), (2, 1.0, 2), (2, 1.0, 1)])
+def test_zero_engine_world2_gloo_matches_single_process_adamw(ga, clip, stage):
     world, steps = 2, 3
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + ga
-    procs = [ctx.Process(target=_worker, args=(r, world, ga, steps, clip, port, q)) for r in range(world)]
+    port = 29600 + ga + 10 * stage
+    procs = [ctx.Process(target=_worker, args=(r, world, ga, steps, clip, port, q, stage)) for r in range(world)]
     for p in procs:
         p.start()
     got = dict(q.get(timeout=120) for _ in range(world))
@@ -150,7 +177,7 @@ def test_zero_engine_world2_gloo_matches_single_process_adamw(ga, clip):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert torch.equal(got[0], got[1]), "ranks disagree on the gathered parameters"
-    ref = _reference(world, ga, steps, 1e-2, 0.1, clip)
+    ref = _reference(world, ga, steps, 1e-2, 0.1, clip, stage)
     # identical arithmetic up to the order of the two-rank bf16 sum -> bit-exact here
     assert torch.equal(got[0], ref), (got[0].float() - ref.float()).abs().max()
 
@@ -166,3 +193,24 @@ def test_engine_rejects_wrong_world_and_micro_count():
         eng.step()
     with pytest.raises(ValueError, match="world_size"):
         ZeroEngine(_ToyModel(2), kernels=K)
+
+
+def test_compact_grads_folds_layer_buckets_onto_rotating_slots():
+    fb = FlatBuffers(_spec(), "cpu", world_size=2)
+    v0 = fb.view("layers.0.w1.weight", grad=True)
+    v2 = fb.view("layers.2.w1.weight", grad=True)
+    v1 = fb.span("layers.1.w1.weight", 128, 24, grad=True)
+    head = fb.view("head.weight", grad=True)
+    full = fb.grads.numel()
+    released = fb.compact_grads(slots=2)
+    layer_len = fb.buckets[fb.bucket_index["layer0"]][2]
+    assert released == 2 * layer_len and fb.grads.numel() == full - layer_len
+    # views handed out before the call were re-pointed in place: layers 0 and 2 alias, layer 1 does not
+    v0.fill_(1.0)
+    assert float(v2.float().sum()) == v2.numel() and float(v1.float().abs().sum()) == 0.0
+    assert float(fb.bucket_view(fb.bucket_index["layer2"], grad=True).float().sum()) == v0.numel()
+    head.fill_(2.0)
+    assert float(fb.bucket_view(fb.bucket_index["head"], grad=True).float().sum()) == 2.0 * head.numel()
+    assert [g for g in fb.rot_group if g] == [("layer", 0), ("layer", 1), ("layer", 0)]
+    # parameters keep their full-size layout
+    assert fb.params.numel() == fb.total
