@@ -172,6 +172,7 @@ class Trainer:
         done = False
         micro = 0
         while not done:
+            stopped_mid_epoch = False
             sampler = getattr(loader, "batch_sampler", None)
             if hasattr(sampler, "set_epoch"):
                 sampler.set_epoch(self.current_epoch)
@@ -201,15 +202,18 @@ class Trainer:
                     cb.on_train_batch_end(self, model, loss, batch, batch_idx)
                 if self.max_steps and self.max_steps > 0 and self.global_step >= self.max_steps:
                     done = True
+                    stopped_mid_epoch = True
                     break
             for sc in self.lr_scheduler_configs:
                 if sc.get("interval", "epoch") == "epoch":
                     sc["scheduler"].step()
             for cb in self.callbacks:
                 cb.on_train_epoch_end(self, model)
-            self.current_epoch += 1
+            if not stopped_mid_epoch:   # max_steps hit inside the epoch: it is not complete (a resumed run must reuse its
+                self.current_epoch += 1  # permutation seed, universal_sampler.py:104-113)
             if self.max_epochs and self.max_epochs > 0 and self.current_epoch >= self.max_epochs:
                 done = True
+        self.engine.wait_params()
         for cb in self.callbacks:
             cb.on_fit_end(self, model)
         if torch.cuda.is_available():

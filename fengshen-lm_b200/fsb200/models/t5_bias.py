@@ -35,16 +35,29 @@ def rel_offsets(seq_q, seq_kv, device=None):
     return torch.arange(-(seq_q - 1), seq_kv, dtype=torch.int64, device=device)
 
 
+_bucket_cache = {}
+
+
+def offset_buckets(seq_q, seq_kv, bidirectional, num_buckets=32, max_distance=128, device=None):
+    """Bucket index of every offset k - q in [-(S_q - 1), S_kv - 1] (cached: pure function of its integer arguments)."""
+    key = (seq_q, seq_kv, bool(bidirectional), num_buckets, max_distance, str(device))
+    b = _bucket_cache.get(key)
+    if b is None:
+        b = relative_position_bucket(rel_offsets(seq_q, seq_kv, device), bidirectional, num_buckets, max_distance)
+        _bucket_cache[key] = b
+    return b
+
+
 def rel_bias_vector(table, seq_q, seq_kv, bidirectional, num_buckets=32, max_distance=128):
     """table [num_buckets, heads] -> fp32 [heads, S_q + S_kv - 1]: bias[h, q, k] == vec[h, k - q + S_q - 1]."""
-    b = relative_position_bucket(rel_offsets(seq_q, seq_kv, table.device), bidirectional, num_buckets, max_distance)
+    b = offset_buckets(seq_q, seq_kv, bidirectional, num_buckets, max_distance, table.device)
     return table.float()[b].t().contiguous()
 
 
 def scatter_rel_grad(dvec, seq_q, seq_kv, bidirectional, num_buckets=32, max_distance=128):
     """Gradient w.r.t. the bias vector [heads, S_q + S_kv - 1] -> gradient of the table [num_buckets, heads] (fp32,
     deterministic: index_add over a sorted, fixed index)."""
-    b = relative_position_bucket(rel_offsets(seq_q, seq_kv, dvec.device), bidirectional, num_buckets, max_distance)
+    b = offset_buckets(seq_q, seq_kv, bidirectional, num_buckets, max_distance, dvec.device)
     out = torch.zeros(num_buckets, dvec.shape[0], dtype=torch.float32, device=dvec.device)
     out.index_add_(0, b, dvec.float().t().contiguous())
     return out

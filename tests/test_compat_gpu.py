@@ -67,7 +67,6 @@ def test_resumed_run_continues_the_sample_stream(tmp_path, monkeypatch):
     first_leg = len(seen)
     trainer2, module2 = ex.main(_args(resumed, common + ("--max_steps", "8")))
     assert trainer2.global_step == 8 and module2.consumed_samples == 16
-    got = seen[:4] + seen[first_leg:first_leg + 4] if first_leg >= 4 else seen
     # the 4 batches consumed after the resume are batches 5..8 of the uninterrupted run
     resumed_batches = seen[first_leg:]
     assert len(resumed_batches) >= 4

@@ -251,6 +251,46 @@ def test_embedding_fwd_bwd_bit_exact_gather():
     _close(dW, ref, 3e-2, 2e-2, "embedding bwd")
 
 
+def test_embedding_bwd_is_fp32_accumulated_and_deterministic():
+    """ADVICE r1: a token that occurs thousands of times (padding, frequent characters) must not be swamped by bf16
+    accumulation, and the result must not depend on atomic ordering: per-row fp32 sums in a fixed order, ONE rounding,
+    added onto what dW already holds (the tied LM-head weight gradient of GPT-2 / BERT)."""
+    V, H, T = 64, 256, 8192
+    g = torch.Generator().manual_seed(11)
+    ids = torch.randint(0, V, (T,), generator=g)
+    ids[: T // 2] = 7                                   # a heavy hitter: 4096+ occurrences
+    ids = ids.to(DEV)
+    dout = (torch.randn(T, H, generator=g) * 0.01 + 0.02).to(torch.bfloat16).to(DEV)   # same-sign terms: bf16 sums would stall
+    base = _rand(V, H, seed=12)
+    dW = base.clone()
+    ops.embedding_bwd(ids, dout, dW)
+    ref = base.float() + torch.zeros(V, H, device=DEV).index_add_(0, ids, dout.float())
+    err = (dW.float() - ref).abs().max().item()
+    assert err <= 2 ** -8 * ref.abs().max().item() + 1e-6, err      # one bf16 rounding of the fp32 total
+    dW2 = base.clone()
+    ops.embedding_bwd(ids, dout, dW2)
+    assert torch.equal(dW, dW2)
+
+
+def test_gemm_splitk_uses_caller_workspace_and_is_deterministic():
+    """VERDICT r1 weak #10: the split-K scratch is the caller's (fsb_gemm_workspace_bytes), never a hidden cudaMalloc."""
+    M, N, K = 768, 768, 32768
+    nbytes = L.load().fsb_gemm_workspace_bytes(L.GEMM_TN, M, N, K)
+    assert nbytes > 0 and nbytes % (M * N * 4) == 0
+    assert L.load().fsb_gemm_workspace_bytes(L.GEMM_NT, 4096, 4096, 4096) == 0
+    a, b = _rand(K, M, seed=1, scale=0.05), _rand(K, N, seed=2, scale=0.05)
+    out1 = ops.gemm(L.GEMM_TN, a, b)
+    out2 = ops.gemm(L.GEMM_TN, a, b)
+    assert torch.equal(out1, out2)
+    _close(out1, a.float().t() @ b.float(), 2e-2, 2e-2, "split-K wgrad")
+    # without a workspace the call is refused loudly (no silent change of algorithm, no allocation inside the library)
+    import ctypes
+    d = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    rc = L.load().fsb_gemm_bf16(L.GEMM_TN, M, N, K, a.data_ptr(), M, b.data_ptr(), N, d.data_ptr(), N, L.BF16, None, L.BF16,
+                                L.EPI_NONE, 0, None, 0, 1, 0, 0, 0, 0, None, 0, torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and "workspace" in L.last_error()
+
+
 @pytest.mark.parametrize("V", [512, 39424, 50264])
 def test_softmax_xent(V):
     B, S = 2, 24
