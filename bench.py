@@ -42,6 +42,11 @@ WORKLOADS = {
                               seq=512, per_gpu=128, micro=32, lr=1e-4, betas=(0.9, 0.999), wd=0.1, clip=1.0, stage=1,
                               label="Erlangshen-MegatronBERT-1.3B MLM+SOP pretrain, seq 512, batch 128/GPU, ZeRO-1 "
                                     "(BASELINE configs[2])"),
+    # Randeng-T5-784M = mT5-large shape: d 1024, 24+24 layers, 16 heads x 64, gated-GeLU d_ff 2816; the
+    # released vocabulary (32598, pretrain_t5.py:90) padded to a multiple of 8; enc / dec 512 as BASELINE words it
+    "randeng-t5-784m": dict(family="t5", vocab_size=32600, d_model=1024, d_kv=64, d_ff=2816, num_layers=24, num_heads=16,
+                            seq=512, seq_dec=512, per_gpu=32, micro=16, lr=1e-4, betas=(0.9, 0.999), wd=0.1, clip=1.0,
+                            label="Randeng-T5-784M seq2seq pretrain, enc 512 / dec 512, batch 32/GPU, ZeRO-2 (BASELINE configs[4])"),
     "ziya-llama-13b": dict(family="llama", vocab_size=39424, hidden_size=5120, num_hidden_layers=40,
                            num_attention_heads=40, seq=2048, per_gpu=32, micro=4, lr=1e-4, betas=(0.9, 0.95), wd=0.1,
                            clip=1.0, label="Ziya-LLaMA-13B pretrain, seq 2048, global batch 32/GPU, ZeRO-2 (BASELINE configs[3])"),
@@ -61,6 +66,9 @@ def workload(name):
 
 def flops_per_token(w):
     """F_tok = 6*N_mm + 3*F_attn_fwd (causal-counted), SURVEY.md §8(d) / BASELINE.md §3."""
+    if w["family"] == "t5":
+        from fsb200.models.t5 import t5_flops_per_step
+        return t5_flops_per_step(w, 1, w["seq"], w["seq_dec"]) / (w["seq"] + w["seq_dec"])   # per (enc + dec) token
     if w["family"] == "gpt2":
         h, L, V, s = w["n_embd"], w["n_layer"], w["vocab_size"], w["seq"]
         n_mm = L * 12 * h * h + V * h
@@ -176,6 +184,10 @@ def make_host_batches(w, n_pool, rank):
     out = []
     for _ in range(n_pool):
         ids = torch.randint(1, w["vocab_size"] - 8, (w["micro"], w["seq"]), generator=g, dtype=torch.int64)
+        if w["family"] == "t5":     # span-corruption-shaped: encoder ids, decoder labels (HF shifts them right itself)
+            lab = torch.randint(1, w["vocab_size"] - 8, (w["micro"], w["seq_dec"]), generator=g, dtype=torch.int64)
+            out.append({"input_ids": ids.pin_memory(), "labels": lab.pin_memory()})
+            continue
         if w["family"] == "bert":   # MLM: labels = -100 except a Bernoulli(0.15) subset; C3 adds NSP labels
             sel = torch.rand(ids.shape, generator=g) < 0.15
             b = {"input_ids": ids.pin_memory(), "labels": torch.where(sel, ids, torch.full_like(ids, -100)).pin_memory(),
@@ -205,6 +217,14 @@ def build_model(w, device, world):
                               hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, initializer_range=0.02)
         cls = MegatronBertForPreTraining if w["variant"] == "megatron" else BertForMaskedLM
         return cls(cfg, device=device, world_size=world)
+    if w["family"] == "t5":
+        from fsb200.models.t5 import MT5ForConditionalGeneration
+        cfg = SimpleNamespace(vocab_size=w["vocab_size"], d_model=w["d_model"], d_kv=w["d_kv"], d_ff=w["d_ff"],
+                              num_layers=w["num_layers"], num_decoder_layers=w["num_layers"], num_heads=w["num_heads"],
+                              relative_attention_num_buckets=32, relative_attention_max_distance=128, dropout_rate=0.0,
+                              feed_forward_proj="gated-gelu", tie_word_embeddings=True, layer_norm_epsilon=1e-6,
+                              pad_token_id=0, decoder_start_token_id=0)
+        return MT5ForConditionalGeneration(cfg, device=device, world_size=world)
     from fsb200.models.llama import LlamaForCausalLM
     cfg = SimpleNamespace(vocab_size=w["vocab_size"], hidden_size=w["hidden_size"],
                           num_hidden_layers=w["num_hidden_layers"], num_attention_heads=w["num_attention_heads"],

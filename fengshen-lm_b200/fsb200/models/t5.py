@@ -63,8 +63,11 @@ class MT5ForConditionalGeneration(nn.Module):
             raise RuntimeError(f"fsb200 MT5: dropout_rate={g('dropout_rate')} — dropout is not implemented; set it to 0")
         if g("feed_forward_proj", "gated-gelu") != "gated-gelu":
             raise RuntimeError("fsb200 MT5: only feed_forward_proj='gated-gelu' (T5 v1.1 / mT5) is implemented")
-        if g("tie_word_embeddings", False):
-            raise RuntimeError("fsb200 MT5: tie_word_embeddings=True (original T5) is not implemented; mT5 / Randeng-T5 untie it")
+        # transformers 5.x FORCES tie_word_embeddings=True for MT5 configs (configuration_mt5.py __post_init__: "we have to tie
+        # always") and applies NO d^-0.5 rescale to the decoder output (modeling_mt5.py:1141-1143) — that is what the reference
+        # script gets from `MT5ForConditionalGeneration(config)` with the installed library, and what the goldens pin. Older
+        # releases honoured mT5's untied head; both are implemented, neither rescales.
+        self.tied = bool(g("tie_word_embeddings", False))
         if self.dk not in (64, 128) or self.V % 8 or self.d % 8 or self.ff % 8:
             raise RuntimeError("fsb200 MT5: d_kv must be 64/128 and vocab/d_model/d_ff multiples of 8 (pad the vocab)")
         d, inner, ff, V = self.d, self.nh * self.dk, self.ff, self.V
@@ -103,7 +106,8 @@ class MT5ForConditionalGeneration(nn.Module):
             spec.add(p + "2.DenseReluDense.wo.weight", (d, ff), bk)
             spec.add(p + "2.layer_norm.weight", (d,), bk)
         spec.add("decoder.final_layer_norm.weight", (d,), "head")
-        spec.add("lm_head.weight", (V, d), "head")
+        if not self.tied:
+            spec.add("lm_head.weight", (V, d), "head")
         self.flat = FlatBuffers(spec, dev, world_size=world_size)
 
         # module tree mirroring HF's parameter names (state_dict / named_parameters / weight-decay grouping BY NAME)
@@ -120,6 +124,10 @@ class MT5ForConditionalGeneration(nn.Module):
                 mod = getattr(mod, part)
             setattr(mod, parts[-1], prm)
 
+        if self.tied:
+            self.lm_head = _Holder()
+            self.lm_head.weight = self._p["shared.weight"]      # same Parameter object: named_parameters() lists it once
+        self._head = "shared.weight" if self.tied else "lm_head.weight"
         fl = self.flat
         E, D = "encoder.block.{}.layer.", "decoder.block.{}.layer."
         self._e_qkv = [fl.span(E.format(i) + "0.SelfAttention.q.weight", 3 * inner, d) for i in range(self.ne)]
@@ -187,7 +195,7 @@ class MT5ForConditionalGeneration(nn.Module):
 
     # ---- engine hooks -----------------------------------------------------------------------------------------------
     def _done(self, bucket):
-        if self.grad_hook is not None:
+        if self.grad_hook is not None and bucket in self.flat.bucket_index:   # "head" does not exist with a tied LM head
             self.grad_hook(bucket)
 
     def _need(self, bucket):
@@ -294,7 +302,7 @@ class MT5ForConditionalGeneration(nn.Module):
                 dacts.append((y, r1, h1, qkv, o, lse, y1, r2, h2, qc, kvc, oc, lsec, y2, r3, h3, gu, act))
             y, prev = y2, m
         hf, rfd, xfd = self._norm(prev, y, "decoder.final_layer_norm.weight")
-        logits = ops.gemm(L.GEMM_NT, hf, P("lm_head.weight").data)
+        logits = ops.gemm(L.GEMM_NT, hf, P(self._head).data)
         loss, ctx = None, None
         if lab is not None:
             keep = logits.clone() if (want_logits and save) else None
@@ -316,9 +324,9 @@ class MT5ForConditionalGeneration(nn.Module):
         self._begin_backward()
         if gloss is not None:
             ops.scale_inplace(dlogits, gloss)
-        Wlm = P("lm_head.weight")
+        Wlm = P(self._head)
         dhf = ops.gemm(L.GEMM_NN, dlogits, Wlm.data)
-        ops.gemm(L.GEMM_TN, dlogits, hf, out=Wlm.main_grad, accumulate=acc)
+        ops.gemm(L.GEMM_TN, dlogits, hf, out=Wlm.main_grad, accumulate=acc)   # tied head: written first, the embeddings add later
         del dlogits
         self._done("head")                      # lm_head is the bucket's only decayed parameter (the norms are no-decay)
         fs = P("decoder.final_layer_norm.weight")
@@ -407,7 +415,7 @@ class MT5ForConditionalGeneration(nn.Module):
                 self._table_grad("encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight", drel_e, Se, True, acc)
             self._done(f"enc{i}")
         Wg = P("shared.weight").main_grad
-        if not acc:
+        if not acc and not self.tied:
             Wg.zero_()
         ops.embedding_bwd(ids, dx, Wg)          # encoder inputs
         ops.embedding_bwd(dec_ids, ddec_emb, Wg)  # decoder inputs share the table

@@ -120,7 +120,9 @@ def train_gpt2(model, batches, steps, lr=1e-3, weight_decay=0.1, warmup=2):
 # examples/pretrain_t5/pretrain_t5.py:57-59 builds transformers.MT5ForConditionalGeneration(MT5Config); training_step
 # (:81-87) is `self.model(input_ids=..., labels=...)` — HF shifts the labels right itself, T5LayerNorm is an RMSNorm without
 # mean subtraction, attention is UNSCALED with an additive relative-position bias shared by all layers of a stack, the FFN is
-# gated-GELU (wi_0, wi_1, wo), nothing has a bias, lm_head is untied for mT5 (tie_word_embeddings=False).
+# gated-GELU (wi_0, wi_1, wo), nothing has a bias. NOTE: transformers 5.x forces tie_word_embeddings=True for MT5 configs
+# (configuration_mt5.py __post_init__), so the model built here — exactly what the reference script would get with this library —
+# has lm_head tied to `shared` (51 parameters) and no d^-0.5 rescale of the decoder output; the keyword below is ignored by 5.x.
 MT5_SMALL = dict(vocab_size=512, d_model=256, d_kv=64, d_ff=512, num_layers=2, num_decoder_layers=2, num_heads=4,
                  relative_attention_num_buckets=32, relative_attention_max_distance=128)
 

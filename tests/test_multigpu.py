@@ -18,7 +18,7 @@ for p in (os.path.join(ROOT, "fengshen-lm_b200"), os.path.join(ROOT, "oracle")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-CFG = dict(V=512, h=256, L=2, nh=4, S=64, steps=5)
+CFG = dict(V=512, h=256, L=3, nh=4, S=64, steps=5)   # 3 layers: the ZeRO-2 gradient slots rotate
 
 
 def _cfg():
@@ -27,7 +27,7 @@ def _cfg():
                            rotary_emb_base=10000, llama_mlp_multiple_of=256)
 
 
-def _run(rank, world, port, q, ga):
+def _run(rank, world, port, q, ga, stage=2):
     import llama_oracle as O
     from fsb200.engine import ZeroEngine
     from fsb200.models.llama import LlamaForCausalLM
@@ -38,7 +38,7 @@ def _run(rank, world, port, q, ga):
     dev = torch.device("cuda", rank)
     model = LlamaForCausalLM(_cfg(), device=dev, world_size=world)
     model.load_reference_state_dict(O.make_weights(CFG["V"], CFG["h"], CFG["L"], seed=0))
-    eng = ZeroEngine(model, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, ga_steps=ga)
+    eng = ZeroEngine(model, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, ga_steps=ga, stage=stage)
     losses = []
     for it in range(CFG["steps"]):
         # global batch of 4 sequences per step; each rank takes its contiguous share, split into `ga` micro-batches
@@ -51,6 +51,7 @@ def _run(rank, world, port, q, ga):
             eng.backward_done()
             step_loss += out.loss.item() / ga
         eng.step()
+        eng.wait_params()
         t = torch.tensor([step_loss], device=dev)
         if world > 1:
             dist.all_reduce(t)
@@ -65,17 +66,21 @@ def _run(rank, world, port, q, ga):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_zero_matches_single_gpu():
+@pytest.mark.parametrize("ga,stage", [(1, 2), (2, 2), (2, 1)])
+def test_two_rank_zero_matches_single_gpu(ga, stage):
+    """ga=2 exercises what ADVICE r1 flagged: the next micro-batch's backward overwrites gradient buckets that the previous
+    micro-batch's reduce-scatter (side stream) read — fenced by the engine's per-bucket events and the backward-begin join;
+    stage 2 also runs the layer buckets through the two rotating gradient slots, stage 1 reduces once per step."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, 2, 29711, q, 1)) for r in range(2)]
+    procs = [ctx.Process(target=_run, args=(r, 2, 29711 + 7 * ga + stage, q, ga, stage)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(2)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    p1 = ctx.Process(target=_run, args=(0, 1, 0, q, 2))   # single GPU, same global batch via 2 micro-batches
+    p1 = ctx.Process(target=_run, args=(0, 1, 0, q, 2 * ga))   # single GPU, same global batch via micro-batches
     p1.start()
     single = q.get(timeout=300)
     p1.join(timeout=60)

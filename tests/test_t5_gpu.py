@@ -32,6 +32,13 @@ def _cuda(b):
     return {k: v.cuda() for k, v in b.items()}
 
 
+def _loss_close(got, want):
+    """HF's MT5 init draws the (tied) embedding / LM head from N(0, 1) and applies no d^-0.5 rescale, so a random-init model has
+    logits of O(100) and a loss of O(150): the bf16 rounding of such logits (2^-8 relative) is what bounds the agreement.
+    Tolerance: 3e-3 absolute (the LLaMA / GPT-2 bar at loss ~6) + 5e-4 relative."""
+    return abs(got - want) <= 3e-3 + 5e-4 * abs(want)
+
+
 def test_mt5_forward_backward_vs_transformers_and_golden():
     g = np.load(GOLD)
     ref = H.build_mt5(H.MT5_SMALL)
@@ -42,7 +49,7 @@ def test_mt5_forward_backward_vs_transformers_and_golden():
     out_ref.loss.backward()
     mine = _mine(ref)
     out = mine(**_cuda(batch), return_logits=True)
-    assert abs(out.loss.item() - out_ref.loss.item()) <= 3e-3, (out.loss.item(), out_ref.loss.item())
+    assert _loss_close(out.loss.item(), out_ref.loss.item()), (out.loss.item(), out_ref.loss.item())
     tol = 4 * 2.0 ** -8 * out_ref.logits.abs().max().item()
     assert (out.logits.float().cpu() - out_ref.logits).abs().max().item() <= tol
     out.loss.backward()
@@ -57,8 +64,32 @@ def test_mt5_forward_backward_vs_transformers_and_golden():
         assert abs(got.norm().item() / (want.norm().item() + 1e-30) - 1.0) <= 0.03, name
         assert abs(want.norm().item() - float(g["gradnorm/" + name])) <= 1e-4 * max(1.0, float(g["gradnorm/" + name])), name
         checked += 1
-    # every parameter of the HF model has a counterpart (embed_tokens are aliases of shared.weight)
-    assert checked == len([n for n in ref_params if "embed_tokens" not in n])
+    # every parameter of the HF model has a counterpart (embed_tokens / the tied lm_head are aliases of shared.weight)
+    assert checked == len(ref_params) == 51
+
+
+def test_mt5_untied_head_variant():
+    """Older transformers releases (and the official mT5 checkpoints) keep lm_head separate from the shared embedding; the
+    installed 5.5 ties it (configuration_mt5.py). The untied path is checked against the same HF model with the head weight
+    cloned: logits and loss only depend on which matrix the head multiplies by."""
+    import copy
+    ref = H.build_mt5(H.MT5_SMALL)
+    batch = H.make_t5_batch(H.MT5_SMALL["vocab_size"], 2, 64, 32, seed=21)
+    cfg = copy.copy(ref.config)
+    cfg.tie_word_embeddings = False
+    mine = MT5ForConditionalGeneration(cfg, device="cuda")
+    sd = dict(ref.state_dict())
+    sd["lm_head.weight"] = ref.shared.weight.detach().clone()
+    mine.load_reference_state_dict(sd)
+    assert "lm_head.weight" in dict(mine.named_parameters())
+    out = mine(**_cuda(batch))
+    assert _loss_close(out.loss.item(), ref(**batch).loss.item())
+    out.loss.backward()
+    g_head = mine.P("lm_head.weight").main_grad.float()
+    g_emb = mine.P("shared.weight").main_grad.float()
+    ref.zero_grad(); ref(**batch).loss.backward()
+    tot = (g_head + g_emb).cpu().flatten(); want = ref.shared.weight.grad.flatten()
+    assert (torch.dot(tot, want) / (tot.norm() * want.norm())).item() >= 0.998
 
 
 @pytest.mark.parametrize("se,sd", [(128, 128), (200, 57)])
@@ -68,7 +99,7 @@ def test_mt5_shapes_and_shift_right(se, sd):
     out_ref = ref(**batch)
     mine = _mine(ref)
     out = mine(**_cuda(batch))
-    assert abs(out.loss.item() - out_ref.loss.item()) <= 3e-3
+    assert _loss_close(out.loss.item(), out_ref.loss.item()), (out.loss.item(), out_ref.loss.item())
     # integer side: decoder inputs are bit-exact with HF's _shift_right
     want = ref._shift_right(batch["labels"])
     assert torch.equal(mine._shift_right(batch["labels"].cuda()).cpu(), want)
@@ -99,14 +130,14 @@ def test_mt5_training_curve_tracks_transformers():
         eng.backward_done()
         eng.step()
         got.append(out.loss.item())
-    err = np.abs(np.array(got) - np.array(want)).max()
-    assert got[-1] < got[0] - 0.5 and err <= 3e-2, (err, got, want)
+    err = (np.abs(np.array(got) - np.array(want)) / np.abs(np.array(want))).max()
+    assert got[-1] < 0.5 * got[0] and err <= 1e-2, (err, got, want)   # relative: the curve runs from ~160 down to ~25
 
 
 def test_mt5_grad_accumulation_rotating_slots_match_full_batch():
     """ZeRO-2 with GA: the enc*/dec* layer buckets share rotating gradient slots; two micro-batches of 2 must give the same
     update as what the fp32 accumulation of their gradients implies (checked against a one-shot batch of 4)."""
-    ref = H.build_mt5(H.MT5_SMALL)
+    ref = H.build_mt5(dict(H.MT5_SMALL, num_layers=3, num_decoder_layers=3))   # >= 3 layers per stack: the slots rotate
     V = H.MT5_SMALL["vocab_size"]
     b4 = H.make_t5_batch(V, 4, 64, 32, seed=90)
     one = _mine(ref)
