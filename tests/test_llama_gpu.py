@@ -6,7 +6,8 @@ keeps bf16 activations with fp32 accumulation, the oracle is fp32 end to end):
   loss            |delta| <= 3e-3   at init (north_star asks 1e-3 on the 20-step curve of an fp32/bf16 run; see curve test)
   logits          |delta| <= 4 * 2^-8 * max|logit|
   gradients       cosine >= 0.999 and norm ratio within 2 % per parameter
-  20-step curve   max |delta| <= 1e-2 against the reference curve (measured 3e-3 / 6e-3; bf16 parameters, fp32 master weights)
+  20-step curve   max |delta| <= 1e-2 against the reference's fp32 curve AND <= 1/3 of |reference bf16 - reference fp32|
+                  (measured 3e-3 / 6e-3 vs 4e-2 for the reference's own bf16 run; see the curve test)
 """
 import glob
 import math
@@ -90,9 +91,17 @@ def test_loss_curve_vs_reference_golden(path):
         eng.step(lr=O.polynomial_lr(it, lr, warm * steps, steps, lr_end))
         curve.append(out.loss.item())
     err = np.abs(np.array(curve) - g["loss_curve"]).max()
-    # measured on B200 (tools/probe_loss_curve.py): 3.0e-3 (hn128; 8.9e-4 relative) and 6.1e-3 (hn64; 2.3e-3 relative) — bf16
-    # parameters / activations against the reference's fp32 CPU run; 1e-2 leaves room for kernel re-tilings
-    assert err <= 1e-2, (err, curve[:3], g["loss_curve"][:3])
+    # north_star asks for 1e-3 against "the reference CPU run". The reference's OWN bf16 run on the CPU (its modules cast to
+    # bfloat16, fp32 master AdamW: `loss_curve_bf16`, oracle/make_golden.py) sits 4.0e-2 / 4.1e-2 (max; 1.5e-2 / 1.7e-2 mean)
+    # away from its fp32 run over these 20 steps — that is the noise floor of bf16 arithmetic on this problem, 40x the
+    # north_star figure. This path (bf16 storage, fp32 accumulation inside every kernel, fp32 master weights) measured
+    # 3.0e-3 (hn128) and 6.1e-3 (hn64) on B200 (tools/probe_loss_curve.py): 7-13x CLOSER to the fp32 reference than the
+    # reference's bf16 arithmetic is. Asserted: within 1e-2 absolute of the fp32 reference curve AND at most a third of the
+    # reference's own bf16-vs-fp32 distance; 1e-3 is not reachable by any bf16 step, and the test says so instead of hiding it.
+    ref16 = np.abs(g["loss_curve_bf16"] - g["loss_curve"]).max()
+    assert ref16 > 1e-2, ref16                      # the noise-floor claim itself is pinned
+    assert err <= 1e-2 and err <= ref16 / 3.0, (err, ref16, curve[:3], g["loss_curve"][:3])
+    print(f"[parity] {os.path.basename(path)}: |gpu - ref_fp32| = {err:.2e}; |ref_bf16 - ref_fp32| = {ref16:.2e}")
 
 
 def test_gradient_accumulation_equals_large_batch():
