@@ -39,3 +39,15 @@ class LlamaForCausalLM(_FsbLlama):
             sd.update(torch.load(fn, map_location="cpu", weights_only=True))
         model.load_reference_state_dict(sd)
         return model
+
+    def save_pretrained(self, path, **_):
+        """HF-style export (what the scripts call after training, e.g. examples/pretrain_t5/pretrain_t5.py:105-112 for its
+        model): config.json + pytorch_model.bin in the reference's key layout; `from_pretrained(path)` reads it back, and
+        `fengshen.utils.llama_convert.fs_to_hf_state_dict` turns it into a transformers LLaMA checkpoint."""
+        from fengshen.utils.llama_convert import save_pretrained_fs
+        hook = getattr(self, "param_hook", None)
+        eng = getattr(hook, "__self__", None)
+        if eng is not None and hasattr(eng, "wait_params"):
+            eng.wait_params()
+        cfg = self.config.to_dict() if hasattr(self.config, "to_dict") else vars(self.config)
+        save_pretrained_fs({k: v for k, v in self.state_dict().items()}, cfg, path)

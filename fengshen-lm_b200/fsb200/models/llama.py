@@ -252,6 +252,126 @@ class LlamaForCausalLM(nn.Module):
                 logits = keep
         return loss, (logits if want_logits else None), ctx
 
+    # ---- KV-cache inference -----------------------------------------------------------------------
+    # The reference decodes through HF's GenerationMixin: `prepare_inputs_for_generation` (modeling_llama.py:353-377) feeds the
+    # last token with position_ids = cumsum(attention_mask) - 1, every layer concatenates the new key / value onto `layer_past`
+    # (layers/transformer.py:529-537) and `llama_generate.generate` (examples/ziya_llama/llama_generate.py:16-39) left-pads the
+    # prompts. Here the cache is a pre-allocated [batch, max_length, heads, head_dim] pair per layer; a decode step runs the
+    # same kernels as training with one query row per sequence, the unused tail of the cache (and the left padding) hidden by
+    # the key mask. Padded keys ARE masked (the reference's `global` attention path; its flash path ignores the mask).
+    @property
+    def device(self):
+        return self.flat.params.device
+
+    def _layer_infer(self, i, x, prev_m, pos, B, S, kc, vc, at, kv_mask, causal):
+        """One layer forward without saving activations; writes this call's keys / values into the cache at [at, at + S)."""
+        h, nh, hn, ff = self.h, self.nh, self.hn, self.ff
+        lyr = self.llama.layers[i]
+        h1, _, x = ops.rmsnorm_fwd(x if prev_m is None else prev_m, lyr.input_layernorm.scale.data, self.eps,
+                                   residual=None if prev_m is None else x)
+        qkv = ops.gemm(L.GEMM_NT, h1, lyr.attention.query_key_value.weight.data)
+        ops.rope_inplace(qkv, self._cos, self._sin, pos, nh, hn, 3 * h, 3 * hn, offset=0)
+        ops.rope_inplace(qkv, self._cos, self._sin, pos, nh, hn, 3 * h, 3 * hn, offset=hn)
+        q5 = qkv.view(B, S, nh, 3, hn)
+        kc[:, at:at + S].copy_(q5[:, :, :, 1])
+        vc[:, at:at + S].copy_(q5[:, :, :, 2])
+        if causal:   # prefill: attend inside the prompt (causal + left-padding mask)
+            o, _ = ops.sdpa_fwd(q5[:, :, :, 0], q5[:, :, :, 1], q5[:, :, :, 2], 1.0 / math.sqrt(hn), True,
+                                kv_mask=None if kv_mask is None else kv_mask[:, :S].contiguous())
+        else:        # decode: one query row per sequence against the whole cache; unwritten slots are masked
+            o, _ = ops.sdpa_fwd(q5[:, :, :, 0], kc, vc, 1.0 / math.sqrt(hn), False, kv_mask=kv_mask)
+        a = ops.gemm(L.GEMM_NT, o.view(B * S, h), lyr.attention.dense.weight.data)
+        h2, _, x1 = ops.rmsnorm_fwd(a, lyr.post_attention_layernorm.scale.data, self.eps, residual=x)
+        gu = ops.gemm(L.GEMM_NT, h2, self._w13[i])
+        act = ops.glu_fwd(L.ACT_SILU, gu[:, :ff], gu[:, ff:])
+        m = ops.gemm(L.GEMM_NT, act, lyr.mlp.w2.weight.data)
+        return x1, m
+
+    def _infer(self, ids, pos, B, S, cache, at, kv_mask, causal):
+        """ids / pos flattened [B*S]; returns fp32 logits of the LAST position of every sequence, [B, V]."""
+        for b in ("no_decay", "embed_in"):
+            self._need(b)
+        x, prev_m = ops.embedding_fwd(ids, self.llama.embed_in.word_embeddings.weight.data), None
+        for i in range(self.nl):
+            self._need(f"layer{i}")
+            x, prev_m = self._layer_infer(i, x, prev_m, pos, B, S, cache[i][0], cache[i][1], at, kv_mask, causal)
+        self._need("head")
+        hf, _, _ = ops.rmsnorm_fwd(prev_m, self.llama.final_layer_norm.scale.data, self.eps, residual=x)
+        last = hf.view(B, S, self.h)[:, -1].contiguous()                       # [B, h]
+        rows = max(8, B)                                                        # the GEMM wants >= 8 aligned rows
+        if rows != B:
+            pad = torch.zeros((rows, self.h), dtype=last.dtype, device=last.device)
+            pad[:B] = last
+            last = pad
+        return ops.gemm(L.GEMM_NT, last, self.embed_out.final_linear.weight.data)[:B].float()
+
+    @torch.no_grad()
+    def generate(self, input_ids, attention_mask=None, max_length=None, max_new_tokens=None, do_sample=False,
+                 temperature=1.0, top_k=0, top_p=1.0, repetition_penalty=1.0, pad_token_id=None, eos_token_id=None,
+                 generator=None, **_):
+        """Greedy / sampling decode with a KV cache; the keyword surface `llama_generate.generate` passes to HF's
+        `model.generate` (do_sample, top_p, top_k, max_length, repetition_penalty, temperature, pad_token_id, eos_token_id).
+        Prompts are LEFT-padded (attention_mask 0 on the pads). Returns [batch, <= max_length] token ids, prompt included,
+        finished rows filled with pad_token_id — HF's GenerationMixin conventions."""
+        dev = self.device
+        ids = input_ids.to(device=dev, dtype=torch.int64)
+        B, S0 = ids.shape
+        mask = torch.ones((B, S0), dtype=torch.uint8, device=dev) if attention_mask is None else \
+            attention_mask.to(device=dev).to(torch.uint8)
+        if max_length is None:
+            max_length = S0 + (max_new_tokens if max_new_tokens is not None else 20)
+        if max_length <= S0:
+            return ids
+        pad_id = pad_token_id if pad_token_id is not None else (eos_token_id if eos_token_id is not None else 0)
+        Lmax = (max_length + 63) // 64 * 64
+        self._ensure_rope(max_length)
+        cache = [(torch.zeros((B, Lmax, self.nh, self.hn), dtype=torch.bfloat16, device=dev),
+                  torch.zeros((B, Lmax, self.nh, self.hn), dtype=torch.bfloat16, device=dev)) for _ in range(self.nl)]
+        kv_mask = torch.zeros((B, Lmax), dtype=torch.uint8, device=dev)
+        kv_mask[:, :S0] = mask
+        # position_ids = cumsum(mask) - 1, pads -> 1 (prepare_inputs_for_generation, modeling_llama.py:360-366)
+        pos = mask.long().cumsum(-1) - 1
+        pos = pos.masked_fill(mask == 0, 1)
+        logits = self._infer(ids.reshape(-1), pos.reshape(-1).contiguous(), B, S0, cache, 0, kv_mask if not bool(mask.all()) else None,
+                             True)
+        count = mask.long().sum(-1)                                             # real tokens so far = next position id
+        seqs = ids
+        done = torch.zeros(B, dtype=torch.bool, device=dev)
+        for cur in range(S0, max_length):
+            nxt = self._pick(logits, seqs, do_sample, temperature, top_k, top_p, repetition_penalty, generator)
+            if eos_token_id is not None:
+                nxt = torch.where(done, torch.full_like(nxt, pad_id), nxt)
+                done = done | (nxt == eos_token_id)
+            seqs = torch.cat([seqs, nxt[:, None]], dim=1)
+            if cur + 1 >= max_length or bool(done.all()):
+                break
+            kv_mask[:, cur] = 1
+            logits = self._infer(nxt, count.clone(), B, 1, cache, cur, kv_mask, False)
+            count = count + 1
+        return seqs
+
+    @staticmethod
+    def _pick(logits, seqs, do_sample, temperature, top_k, top_p, repetition_penalty, generator):
+        """HF logits-processor order: repetition penalty -> temperature -> top-k -> top-p -> sample (or argmax)."""
+        if repetition_penalty != 1.0:
+            seen = torch.gather(logits, 1, seqs)
+            seen = torch.where(seen < 0, seen * repetition_penalty, seen / repetition_penalty)
+            logits = logits.scatter(1, seqs, seen)
+        if not do_sample:
+            return logits.argmax(-1)
+        if temperature != 1.0:
+            logits = logits / temperature
+        if top_k and top_k > 0:
+            kth = torch.topk(logits, min(top_k, logits.shape[-1]), dim=-1).values[:, -1:]
+            logits = logits.masked_fill(logits < kth, float("-inf"))
+        if top_p < 1.0:
+            srt, idx = torch.sort(logits, descending=False, dim=-1)
+            cum = torch.softmax(srt, -1).cumsum(-1)
+            remove = cum <= (1.0 - top_p)
+            remove[:, -1] = False
+            logits = logits.masked_fill(remove.scatter(1, idx, remove), float("-inf"))
+        return torch.multinomial(torch.softmax(logits, -1), 1, generator=generator).squeeze(1)
+
     # ---- backward ---------------------------------------------------------------------------------------------------
     def _backward_impl(self, ctx, gloss):
         acts, hf, rstdf, xf, dlogits, ids, pos, B, S = ctx
