@@ -17,6 +17,8 @@
 // when the true row max exceeds it by more than 2^8 (lazy rescaling): then — rarely — the group multiplies its O rows
 // in TMEM by 2^(m_ref_old - m_new) (tcgen05.ld / tcgen05.st). Probabilities are therefore <= 256 instead of <= 1, well
 // inside bf16/fp32 range; the final O / l is exact in the same way as with the eager rescale.
+#include <stdlib.h>
+
 #include "host_common.h"
 #include "ptx.cuh"
 
@@ -29,6 +31,16 @@ constexpr int ATT_GROUP = 128;                       // softmax threads per Q ti
 constexpr int ATT_THREADS = ATT_NQ * ATT_GROUP + 128; // + warpgroup 2: TMA warp, MMA warp, two idle warps (setmaxnreg donors)
 constexpr int ATT_W_TMA = 8, ATT_W_MMA = 9;
 constexpr float ATT_RESCALE_TAU = 8.0f;              // log2 units
+// setmaxnreg split (a warpgroup shares one value): 256 softmax threads x ATT_SM_REGS + 128 (TMA / MMA / idle) x ATT_WG2_REGS
+// <= 65536. The softmax threads hold two 64-score register sets (S(j) and the prefetched S(j+1)): every register they do not
+// get shows up as local-memory traffic in the hot loop.
+#ifndef ATT_WG2_REGS
+#define ATT_WG2_REGS 48
+#endif
+#ifndef ATT_SM_REGS
+#define ATT_SM_REGS 232
+#endif
+static_assert(256 * ATT_SM_REGS + 128 * ATT_WG2_REGS <= 65536, "register file");
 
 template <int D>
 struct AttFwdSmem {
@@ -67,7 +79,11 @@ __device__ long long g_fwd_trace[2][64][8];
 #define FTRACE(role, step, k) do { } while (0)
 #endif
 
-template <int D, bool kBias>
+// kPT: P(j) is handed to the PV product through TENSOR MEMORY — each softmax thread writes its row's 64 probabilities (bf16
+// pairs, 32 columns) over the first half of the S(j) columns it has just consumed and the tensor core reads the A operand
+// from there (tcgen05.mma with a TMEM A operand, as the backward kernels do for dS): per 64-key step and Q tile that removes a
+// 16 KB shared-memory write, a 16 KB operand read and the generic->async proxy fence from the shared-memory-bound loop.
+template <int D, bool kBias, bool kPT>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttFwdParams p) {
@@ -130,12 +146,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  // register split: 256 softmax threads * 216 + 128 (TMA / MMA / idle) * 72 = 384 * 168
+  // register split: see ATT_SM_REGS / ATT_WG2_REGS
   if (warp > ATT_W_MMA) {
-    reg_dec<72>();   // idle donor warps
+    reg_dec<ATT_WG2_REGS>();   // idle donor warps
   } else if (warp == ATT_W_TMA) {
     // ===================== TMA producer =====================
-    reg_dec<72>();
+    reg_dec<ATT_WG2_REGS>();
     if (lane == 0) {
       const int qc = head * p.q_head_stride, kc = head * p.k_head_stride, vc = head * p.v_head_stride;
       const int active = (n_kv[0] > 0) + (n_kv[1] > 0);
@@ -166,7 +182,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == ATT_W_MMA) {
     // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
-    reg_dec<72>();
+    reg_dec<ATT_WG2_REGS>();
     const uint64_t dsc_q = make_smem_desc_sw128(smem_u32(smem + S::OFF_Q), 0, 1024);
     const uint64_t dsc_k = make_smem_desc_sw128(smem_u32(smem + S::OFF_K), 0, 1024);
     const uint64_t dsc_p = make_smem_desc_sw128(smem_u32(smem + S::OFF_P), 0, 1024);
@@ -181,10 +197,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
     auto issue_PV = [&](int slot, int buf, int st, bool accumulate) {
       const uint64_t da = dsc_p + uint64_t(slot * 2 + buf) * (S::P_BYTES >> 4), db = dsc_v + uint64_t(st) * (S::KV_BYTES >> 4);
+      const uint32_t ta = tmem_base + slot * SLOT_COLS + buf * ATT_BKV;   // P(j): 8 columns per 16-key slice
 #pragma unroll
-      for (int kk = 0; kk < ATT_BKV / 16; ++kk)
-        umma_bf16(tmem_base + slot * SLOT_COLS + 2 * ATT_BKV, da + ((kk * 32) >> 4), db + ((kk * 2048) >> 4), IDESC_PV,
-                  (accumulate || kk != 0) ? 1u : 0u);
+      for (int kk = 0; kk < ATT_BKV / 16; ++kk) {
+        if constexpr (kPT)
+          umma_bf16_ts(tmem_base + slot * SLOT_COLS + 2 * ATT_BKV, ta + 8 * kk, db + ((kk * 2048) >> 4), IDESC_PV,
+                       (accumulate || kk != 0) ? 1u : 0u);
+        else
+          umma_bf16(tmem_base + slot * SLOT_COLS + 2 * ATT_BKV, da + ((kk * 32) >> 4), db + ((kk * 2048) >> 4), IDESC_PV,
+                    (accumulate || kk != 0) ? 1u : 0u);
+      }
       umma_commit(&o_done[slot]);
     };
     mbar_wait(q_full, 0);
@@ -230,7 +252,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ===================== softmax groups: one thread per query row =====================
-    reg_inc<216>();
+    reg_inc<ATT_SM_REGS>();
     const int slot = warp >> 2;
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may access (= warp id % 4)
     const int r_in = quad * 32 + lane;            // row inside the tile == TMEM lane
@@ -320,21 +342,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // prefetch S(j+1) into the other register set while this step's exponentials run
       if (j + 1 < n_mine) load_s(j + 1, nxt);
       FTRACE(0, j, 4);
-      uint8_t* sP = smem + S::OFF_P + (slot * 2 + buf) * S::P_BYTES + r_in * 128;
+      if constexpr (kPT) {
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {            // 8 keys -> one 16-byte chunk of the 128B-swizzled P row
-        uint32_t pk[4];
+        for (int hf = 0; hf < 2; ++hf) {          // 32 keys -> 16 TMEM columns per store (keeps the register footprint low)
+          uint32_t pk[16];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float a = ex2_approx(fmaf(__uint_as_float(cur[ch * 8 + 2 * e]), sc_eff, neg_m));
-          const float bq = ex2_approx(fmaf(__uint_as_float(cur[ch * 8 + 2 * e + 1]), sc_eff, neg_m));
-          pk[e] = pack_bf16x2(a, bq);
-          l0 += a; l1 += bq;                      // fp32 sums of the unrounded probabilities (LSE exact to fp32)
+          for (int e = 0; e < 16; ++e) {
+            const float a = ex2_approx(fmaf(__uint_as_float(cur[hf * 32 + 2 * e]), sc_eff, neg_m));
+            const float bq = ex2_approx(fmaf(__uint_as_float(cur[hf * 32 + 2 * e + 1]), sc_eff, neg_m));
+            pk[e] = pack_bf16x2(a, bq);
+            l0 += a; l1 += bq;                    // fp32 sums of the unrounded probabilities (LSE exact to fp32)
+          }
+          tmem_st16(t_slot + buf * ATT_BKV + hf * 16, pk);   // over the S(j) columns this thread has already consumed
         }
-        *reinterpret_cast<uint4*>(sP + ((ch ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        FTRACE(0, j, 5);
+        tmem_st_wait();
+      } else {
+        uint8_t* sP = smem + S::OFF_P + (slot * 2 + buf) * S::P_BYTES + r_in * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {            // 8 keys -> one 16-byte chunk of the 128B-swizzled P row
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = ex2_approx(fmaf(__uint_as_float(cur[ch * 8 + 2 * e]), sc_eff, neg_m));
+            const float bq = ex2_approx(fmaf(__uint_as_float(cur[ch * 8 + 2 * e + 1]), sc_eff, neg_m));
+            pk[e] = pack_bf16x2(a, bq);
+            l0 += a; l1 += bq;                      // fp32 sums of the unrounded probabilities (LSE exact to fp32)
+          }
+          *reinterpret_cast<uint4*>(sP + ((ch ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        FTRACE(0, j, 5);
+        fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       }
-      FTRACE(0, j, 5);
-      fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();     // order our tcgen05.ld/st before the MMAs that read / overwrite TMEM
       mbar_arrive(&p_ready[slot * 2 + buf]);
       FTRACE(0, j, 6);
@@ -389,12 +428,12 @@ int make_attn_tmap(CUtensorMap* tm, const void* base, int64_t row_stride, int64_
   return make_tmap_bf16(tm, base, 3, dims, strides, box);
 }
 
-template <int D, bool kBias>
+template <int D, bool kBias, bool kPT>
 static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttFwdParams& p,
                            cudaStream_t st) {
   using S = AttFwdSmem<D>;
   static bool configured = false;
-  auto kern = attn_fwd_kernel<D, kBias>;
+  auto kern = attn_fwd_kernel<D, kBias, kPT>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) {
@@ -445,9 +484,11 @@ extern "C" int fsb_sdpa_fwd(const void* q, const void* k, const void* v, void* o
   p.seq_q = int(seq_q); p.seq_kv = int(seq_kv); p.nheads = nheads; p.batch = int(batch);
   p.causal = causal;
   p.scale_log2 = scale * 1.4426950408889634f;
-  if (rel_bias != nullptr)
-    return head_dim == 128 ? launch_attn_fwd<128, true>(tq, tk, tv, p, (cudaStream_t)st)
-                           : launch_attn_fwd<64, true>(tq, tk, tv, p, (cudaStream_t)st);
-  return head_dim == 128 ? launch_attn_fwd<128, false>(tq, tk, tv, p, (cudaStream_t)st)
-                         : launch_attn_fwd<64, false>(tq, tk, tv, p, (cudaStream_t)st);
+  // FSB_ATTN_P_TMEM=0 selects the shared-memory P hand-over (A/B measurements); default: through tensor memory
+  static const bool p_tmem = [] { const char* e = getenv("FSB_ATTN_P_TMEM"); return e ? atoi(e) != 0 : true; }();
+#define FSB_FWD(DD, BB) (p_tmem ? launch_attn_fwd<DD, BB, true>(tq, tk, tv, p, (cudaStream_t)st) \
+                                : launch_attn_fwd<DD, BB, false>(tq, tk, tv, p, (cudaStream_t)st))
+  if (rel_bias != nullptr) return head_dim == 128 ? FSB_FWD(128, true) : FSB_FWD(64, true);
+  return head_dim == 128 ? FSB_FWD(128, false) : FSB_FWD(64, false);
+#undef FSB_FWD
 }

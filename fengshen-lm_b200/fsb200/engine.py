@@ -30,7 +30,7 @@ import torch.distributed as dist
 
 class ZeroEngine:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1, grad_clip=0.0, ga_steps=1,
-                 process_group=None, stage=2, kernels=None, overlap_comm=True, comm_sms=None):
+                 process_group=None, stage=2, kernels=None, overlap_comm=True, comm_sms=None, comm_backend="torch"):
         self.model = model
         self.flat = model.flat
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -74,6 +74,17 @@ class ZeroEngine:
         self.micro = 0
         self.step_count = 0
         self.comm_bytes = 0
+        # Data-path collectives: torch.distributed's NCCL communicator (default), or the library's own fsb_comm_* entry
+        # points (comm_backend="fsb": the C-ABI a non-PyTorch host binds; torch.distributed then only carries the
+        # 128-byte NCCL id at start-up).
+        self.fsb_comm = None
+        if comm_backend not in ("torch", "fsb"):
+            raise ValueError(f"comm_backend {comm_backend!r}: expected 'torch' or 'fsb'")
+        if comm_backend == "fsb" and self.world > 1:
+            if dev.type != "cuda":
+                raise RuntimeError("comm_backend='fsb' needs CUDA devices (NCCL)")
+            from . import comm as _comm
+            self.fsb_comm = _comm.Communicator(self.world, self.rank, process_group, dev)
         # buckets in the order the forward pass first touches them (no-decay parameters — norms, biases — are read by
         # every layer, so that bucket is gathered first)
         order = list(range(nb))
@@ -137,7 +148,7 @@ class ZeroEngine:
                 cur = torch.cuda.current_stream(self.device)
                 self.comm_stream.wait_stream(cur)
                 with torch.cuda.stream(self.comm_stream):
-                    dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=self.pg)
+                    self._reduce_scatter(out, full)
                     if self.acc32 is not None:
                         self.k.accumulate(self._seg(self.acc32, i), out, 1.0, overwrite=first)
                     ev = torch.cuda.Event()
@@ -152,12 +163,24 @@ class ZeroEngine:
                         cur.wait_event(prev)
                     self._last_rot_event[rot[0]] = ev
             else:
-                dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=self.pg)
+                self._reduce_scatter(out, full)
                 if self.acc32 is not None:
                     self.k.accumulate(self._seg(self.acc32, i), out, 1.0, overwrite=first)
             self.comm_bytes += full.numel() * 2 * (self.world - 1) // self.world
         elif self.acc32 is not None:
             self.k.accumulate(self._seg(self.acc32, i), self.flat.bucket_view(i, grad=True), 1.0, overwrite=first)
+
+    def _reduce_scatter(self, out, full):
+        if self.fsb_comm is not None:
+            self.fsb_comm.reduce_scatter(out, full)
+        else:
+            dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _all_gather(self, full, mine):
+        if self.fsb_comm is not None:
+            self.fsb_comm.all_gather(full, mine)
+        else:
+            dist.all_gather_into_tensor(full, mine, group=self.pg)
 
     def backward_done(self):
         """Call once after each micro-batch's loss.backward()."""
@@ -194,7 +217,10 @@ class ZeroEngine:
             for i in range(nb):
                 self.k.sumsq(self._grad_seg(i), self.sumsq, accumulate=(i > 0))
             if self.world > 1:
-                dist.all_reduce(self.sumsq, op=dist.ReduceOp.SUM, group=self.pg)
+                if self.fsb_comm is not None:
+                    self.fsb_comm.all_reduce(self.sumsq)
+                else:
+                    dist.all_reduce(self.sumsq, op=dist.ReduceOp.SUM, group=self.pg)
             self.k.clip_coef(self.sumsq, self.grad_clip, self.coef, self.grad_norm)
             coef = self.coef
         self.step_count += 1
@@ -210,13 +236,12 @@ class ZeroEngine:
                 if self.use_streams:
                     self.comm_stream.wait_stream(cur)
                     with torch.cuda.stream(self.comm_stream):
-                        dist.all_gather_into_tensor(self.flat.bucket_view(i), self.flat.bucket_slice(i, self.rank),
-                                                    group=self.pg)
+                        self._all_gather(self.flat.bucket_view(i), self.flat.bucket_slice(i, self.rank))
                         ev = torch.cuda.Event()
                         ev.record(self.comm_stream)
                     self.ag_event[i] = ev
                 else:
-                    dist.all_gather_into_tensor(self.flat.bucket_view(i), self.flat.bucket_slice(i, self.rank), group=self.pg)
+                    self._all_gather(self.flat.bucket_view(i), self.flat.bucket_slice(i, self.rank))
                 self.comm_bytes += self.flat.buckets[i][2] * 2 * (self.world - 1) // self.world
         self.micro = 0
         self.model.accumulate_grads = False

@@ -73,6 +73,12 @@ SIGNATURES = {
     "fsb_scaled_upper_triang_masked_softmax_fwd": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_f32, c_void_p]),
     "fsb_scaled_upper_triang_masked_softmax_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_i64, c_f32, c_void_p]),
     "fsb_softmax_get_batch_per_block": (c_int, [c_i64, c_i64, c_i64, c_i64]),
+    "fsb_comm_unique_id": (c_int, [c_void_p]),
+    "fsb_comm_init": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "fsb_comm_destroy": (c_int, [c_void_p]),
+    "fsb_comm_reduce_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "fsb_comm_all_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "fsb_comm_all_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "fsb_sdpa_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int,
                              c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_void_p, c_void_p,
                              c_void_p]),
@@ -117,7 +123,8 @@ def check(rc, what):
 
 kernel_launches = 0  # number of __global__ launches issued by the library on behalf of this process
 # kernels launched per successful entry-point call (everything not listed launches exactly one)
-_NO_KERNEL = {"fsb_set_reserved_sms"}
+_NO_KERNEL = {"fsb_set_reserved_sms", "fsb_comm_unique_id", "fsb_comm_init", "fsb_comm_destroy", "fsb_comm_reduce_scatter",
+              "fsb_comm_all_gather", "fsb_comm_all_reduce"}   # host-only calls / NCCL's kernels, not ours
 _KERNELS_PER_CALL = {"fsb_rmsnorm_bwd": 2, "fsb_layernorm_bwd": 2, "fsb_softmax_xent_fwd_bwd": 3, "fsb_sdpa_bwd": 3,
                      "fsb_sumsq": 2, "fsb_colsum": 2, "fsb_act_bwd_bias": 2}
 

@@ -237,6 +237,22 @@ int fsb_sdpa_bwd(const void* q, const void* k, const void* v, const void* o, con
                  float scale, int causal, const uint8_t* kv_mask, const float* rel_bias, float* drel_bias,
                  void* workspace, size_t workspace_bytes, fsb_stream_t stream);
 
+/* ---- communication (NCCL over NVLink / NVSwitch) --------------------------------------------------------------
+ * The three exchange steps of the ZeRO-1/2 data path — the collectives the reference delegates to DeepSpeed
+ * (fengshen/strategies/megatron_deepspeed.py:302-320; Appendix D): bucketed gradient reduce-scatter (SUM), the fp32 scalar
+ * all-reduce of the squared gradient norm, and the in-place parameter all-gather. One communicator per process (= per GPU);
+ * rank 0 creates the 128-byte id with fsb_comm_unique_id and the host distributes it out of band (MPI, a file, a TCP store).
+ * All calls are asynchronous on `stream` (the engine issues them on a dedicated side stream, fenced with events against
+ * the compute stream). In-place forms are allowed where NCCL allows them (all_gather: send == recv + rank * send_count).
+ * NCCL is loaded at run time (dlopen "libnccl.so.2"); if it is absent every fsb_comm_* call fails with FSB_ERR_INVALID. */
+typedef void* fsb_comm_t;
+int fsb_comm_unique_id(void* id128);
+int fsb_comm_init(fsb_comm_t* comm, const void* id128, int world, int rank);
+int fsb_comm_destroy(fsb_comm_t comm);
+int fsb_comm_reduce_scatter(fsb_comm_t comm, const void* send, void* recv, int64_t recv_count, int dtype, fsb_stream_t stream);
+int fsb_comm_all_gather(fsb_comm_t comm, const void* send, void* recv, int64_t send_count, int dtype, fsb_stream_t stream);
+int fsb_comm_all_reduce(fsb_comm_t comm, const void* send, void* recv, int64_t count, int dtype, fsb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

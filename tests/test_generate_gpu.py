@@ -53,12 +53,14 @@ def test_greedy_decode_matches_oracle_token_ids():
     got = model.generate(prompt.cuda(), max_length=21 + steps, do_sample=False).cpu()
     assert got.shape == want.shape
     assert torch.equal(got[:, :21], prompt)
-    for b in range(3):   # identical until (if ever) the oracle itself is undecided at bf16 resolution
+    compared = 0
+    for b in range(3):   # identical until (if ever) the oracle itself is undecided at bf16 resolution; then the row may fork
         for t in range(steps):
             if margins[b, t] < 0.05 * 8:
                 break
             assert got[b, 21 + t] == want[b, 21 + t], (b, t, margins[b, t].item())
-        assert t >= 4, "no decisive step to compare"
+            compared += 1
+    assert compared >= 8, f"only {compared} decisive steps to compare"
 
 
 def test_cached_step_logits_equal_uncached_forward_and_left_padding_is_masked():

@@ -27,7 +27,7 @@ def _cfg():
                            rotary_emb_base=10000, llama_mlp_multiple_of=256)
 
 
-def _run(rank, world, port, q, ga, stage=2):
+def _run(rank, world, port, q, ga, stage=2, backend="torch"):
     import llama_oracle as O
     from fsb200.engine import ZeroEngine
     from fsb200.models.llama import LlamaForCausalLM
@@ -38,7 +38,7 @@ def _run(rank, world, port, q, ga, stage=2):
     dev = torch.device("cuda", rank)
     model = LlamaForCausalLM(_cfg(), device=dev, world_size=world)
     model.load_reference_state_dict(O.make_weights(CFG["V"], CFG["h"], CFG["L"], seed=0))
-    eng = ZeroEngine(model, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, ga_steps=ga, stage=stage)
+    eng = ZeroEngine(model, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, ga_steps=ga, stage=stage, comm_backend=backend)
     losses = []
     for it in range(CFG["steps"]):
         # global batch of 4 sequences per step; each rank takes its contiguous share, split into `ga` micro-batches
@@ -66,14 +66,16 @@ def _run(rank, world, port, q, ga, stage=2):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("ga,stage", [(1, 2), (2, 2), (2, 1)])
-def test_two_rank_zero_matches_single_gpu(ga, stage):
+@pytest.mark.parametrize("ga,stage,backend", [(1, 2, "torch"), (2, 2, "torch"), (2, 1, "torch"), (2, 2, "fsb")])
+def test_two_rank_zero_matches_single_gpu(ga, stage, backend):
     """ga=2 exercises what ADVICE r1 flagged: the next micro-batch's backward overwrites gradient buckets that the previous
     micro-batch's reduce-scatter (side stream) read — fenced by the engine's per-bucket events and the backward-begin join;
     stage 2 also runs the layer buckets through the two rotating gradient slots, stage 1 reduces once per step."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, 2, 29711 + 7 * ga + stage, q, ga, stage)) for r in range(2)]
+    # backend "fsb": the collectives go through the C ABI's fsb_comm_* entry points (NCCL resolved by libfsb200.so itself)
+    port = 29711 + 7 * ga + stage + (40 if backend == "fsb" else 0)
+    procs = [ctx.Process(target=_run, args=(r, 2, port, q, ga, stage, backend)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(2)]

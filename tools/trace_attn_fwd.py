@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 csrc = os.path.join(ROOT, "fengshen-lm_b200", "csrc")
-out = os.path.join(ROOT, "fengshen-lm_b200", "build", "libfsb200_trace.so")   # build it on the CPU box: make -C csrc trace
+out = os.path.join(ROOT, "fengshen-lm_b200", "fsb200", "lib", "libfsb200_trace.so")   # build it on the CPU box: make -C csrc trace
 if not os.path.exists(out):
     raise SystemExit("build the traced library first: make -C fengshen-lm_b200/csrc trace")
 sys.path.insert(0, os.path.join(ROOT, "fengshen-lm_b200"))
