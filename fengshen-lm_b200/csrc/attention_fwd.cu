@@ -35,12 +35,14 @@ constexpr float ATT_RESCALE_TAU = 8.0f;              // log2 units
 // <= 65536. The softmax threads hold two 64-score register sets (S(j) and the prefetched S(j+1)): every register they do not
 // get shows up as local-memory traffic in the hot loop.
 #ifndef ATT_WG2_REGS
-#define ATT_WG2_REGS 48
+#define ATT_WG2_REGS 72
 #endif
 #ifndef ATT_SM_REGS
-#define ATT_SM_REGS 232
+#define ATT_SM_REGS 216
 #endif
-static_assert(256 * ATT_SM_REGS + 128 * ATT_WG2_REGS <= 65536, "register file");
+// 216 / 72 leaves 1024 registers of the SM unclaimed. Do NOT close that gap: 232 / 48 (exactly 65536) never gets its
+// setmaxnreg.inc granted and the kernel hangs (measured the hard way, round 2).
+static_assert(256 * ATT_SM_REGS + 128 * ATT_WG2_REGS <= 65536 - 1024, "register file (keep the launch-time slack)");
 
 template <int D>
 struct AttFwdSmem {
