@@ -19,6 +19,10 @@ class LlamaForCausalLM(_FsbLlama):
             if have != want:
                 raise NotImplementedError(f"fsb200 LlamaForCausalLM: config.{k}={have!r} is outside the Ziya-LLaMA "
                                           f"hot path (only {want!r} is implemented)")
+        if "tp_group" not in kw:   # built inside LightningModule.setup(), after the strategy initialised mpu (as the reference)
+            from fengshen.models.megatron import mpu
+            if mpu.get_model_parallel_world_size() > 1:
+                kw["tp_group"] = mpu.get_model_parallel_group()
         super().__init__(config, **kw)
 
     @classmethod

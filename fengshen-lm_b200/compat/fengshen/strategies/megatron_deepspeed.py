@@ -13,16 +13,15 @@ class DeepSpeedStrategy(OriginDeepSpeedStrategy):
 
     def __init__(self, pipe_model_parallel_size, tensor_model_parallel_size, mpu_seed, accelerator=None,
                  zero_optimization=True, stage=2, **kwargs):
-        if pipe_model_parallel_size != 1 or tensor_model_parallel_size != 1:
-            raise NotImplementedError("fsb200: pipe/tensor model parallel sizes must be 1 on the data-parallel hot path "
-                                      "(tensor parallelism is SURVEY.md §8f rank 1)")
+        if pipe_model_parallel_size != 1:
+            raise NotImplementedError("fsb200: pipe_model_parallel_size must be 1 (pipeline parallelism is outside the hot path)")
         super().__init__(accelerator=accelerator, zero_optimization=zero_optimization, stage=stage, **kwargs)
         self.pipe_model_parallel_size = pipe_model_parallel_size
         self.tensor_model_parallel_size = tensor_model_parallel_size
         self.mpu_seed = mpu_seed
 
     def setup_mpu(self, trainer):
-        """megatron_deepspeed.py:339-369 at TP = PP = 1: load the kernels, register the (trivial) groups, seed."""
+        """megatron_deepspeed.py:339-369 at PP = 1: load the kernels, build the tensor- / data-parallel groups, seed."""
         fused_kernels.load_fused_kernels()
         mpu.initialize_model_parallel(self.tensor_model_parallel_size, self.pipe_model_parallel_size)
         if "activation_checkpointing" in self.config:  # accepted and ignored: the reference never recomputes (SURVEY §2.4)

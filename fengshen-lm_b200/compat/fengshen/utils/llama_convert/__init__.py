@@ -67,3 +67,41 @@ def save_pretrained_fs(state_dict, config, path):
     with open(os.path.join(path, "config.json"), "w") as f:
         json.dump(cfg, f, indent=1)
     torch.save({k: v.detach().cpu() for k, v in state_dict.items()}, os.path.join(path, "pytorch_model.bin"))
+
+
+def split_state_dict_tp(fs_sd, tp, num_heads):
+    """The shard layout of utils/llama_convert/convert_fs_llama_tp.py:143-181 (`part_{rank}` directories): embedding and LM head
+    split along the vocabulary (dim 0); query_key_value viewed as [tp, heads/tp * 3 * head_dim, hidden] (whole heads per rank,
+    interleave kept); dense and w2 split along their INPUT dim (dim 1, row-parallel); w1 / w3 along dim 0 (column-parallel);
+    norms and inv_freq duplicated. Returns a list of `tp` state dicts."""
+    out = [dict() for _ in range(tp)]
+    for k, v in fs_sd.items():
+        if k in ("llama.embed_in.word_embeddings.weight", "embed_out.final_linear.weight"):
+            parts = v.chunk(tp, dim=0)
+        elif "query_key_value" in k:
+            parts = v.view(tp, v.shape[0] // tp, *v.shape[1:]).unbind(0)
+        elif k.endswith("attention.dense.weight") or k.endswith("mlp.w2.weight"):
+            parts = v.chunk(tp, dim=1)
+        elif k.endswith("mlp.w1.weight") or k.endswith("mlp.w3.weight"):
+            parts = v.chunk(tp, dim=0)
+        else:   # layernorm scales, rotary inv_freq: duplicated
+            parts = [v] * tp
+        for r in range(tp):
+            out[r][k] = parts[r].clone()
+    return out
+
+
+def merge_state_dict_tp(shards, num_heads):
+    """Inverse of split_state_dict_tp (what fs_merge_weight.py does for released shards)."""
+    tp = len(shards)
+    out = {}
+    for k in shards[0]:
+        vs = [s[k] for s in shards]
+        if k in ("llama.embed_in.word_embeddings.weight", "embed_out.final_linear.weight") or "query_key_value" in k \
+                or k.endswith("mlp.w1.weight") or k.endswith("mlp.w3.weight"):
+            out[k] = torch.cat(vs, dim=0)
+        elif k.endswith("attention.dense.weight") or k.endswith("mlp.w2.weight"):
+            out[k] = torch.cat(vs, dim=1)
+        else:
+            out[k] = vs[0].clone()
+    return out

@@ -147,7 +147,13 @@ class Trainer:
         self.optimizers, self.lr_scheduler_configs = self._unpack_optimizers(model.configure_optimizers())
         opt = self.optimizers[0]
         fsb_model = self._find_fsb_model(model)
-        if fsb_model.flat.world_size != self.world_size:
+        tp_group = getattr(fsb_model, "tp_group", None)
+        tp = getattr(fsb_model, "tp", 1)
+        dp_group = None
+        if tp > 1:   # tensor parallelism: ZeRO shards over the data-parallel group (ranks with the same tensor-parallel rank)
+            from fengshen.models.megatron import mpu
+            dp_group = mpu.get_data_parallel_group()
+        if fsb_model.flat.world_size != self.world_size // tp:
             raise RuntimeError(f"model laid out for world_size {fsb_model.flat.world_size}, job has {self.world_size}; "
                                "construct the model inside LightningModule.setup() (as the reference scripts do)")
         g0 = opt.param_groups[0]
@@ -157,7 +163,8 @@ class Trainer:
         self.engine = ZeroEngine(fsb_model, lr=g0["lr"], betas=betas, eps=g0.get("eps", 1e-8), weight_decay=wd,
                                  grad_clip=clip, ga_steps=self.accumulate_grad_batches,
                                  stage=getattr(self.strategy, "stage", 2),
-                                 overlap_comm=getattr(self.strategy, "overlap_comm", True))
+                                 overlap_comm=getattr(self.strategy, "overlap_comm", True),
+                                 process_group=dp_group, tp_group=tp_group)
         ckpt_path = ckpt_path or self.resume_from_checkpoint
         if ckpt_path:
             self._load_checkpoint(ckpt_path)

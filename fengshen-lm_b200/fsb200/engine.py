@@ -30,7 +30,7 @@ import torch.distributed as dist
 
 class ZeroEngine:
     def __init__(self, model, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.1, grad_clip=0.0, ga_steps=1,
-                 process_group=None, stage=2, kernels=None, overlap_comm=True, comm_sms=None, comm_backend="torch"):
+                 process_group=None, stage=2, kernels=None, overlap_comm=True, comm_sms=None, comm_backend="torch", tp_group=None):
         self.model = model
         self.flat = model.flat
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -58,6 +58,13 @@ class ZeroEngine:
         # stage 2 accumulates reduced shards in fp32 across micro-batches; stage 1 accumulates full bf16 gradients in place
         self.acc32 = torch.zeros(n, dtype=torch.float32, device=dev) if (self.ga_steps > 1 and self.stage == 2) else None
         self.recv16 = torch.zeros(n, dtype=torch.bfloat16, device=dev) if self.world > 1 else None
+        # tensor parallelism: `process_group` is the DATA-parallel group; the gradient norm also sums over `tp_group`, with
+        # the buckets every tensor-parallel rank holds identically (model.tp_replicated_buckets: norms) counted once
+        self.tp_group = tp_group
+        self.tp = dist.get_world_size(tp_group) if tp_group is not None else 1
+        rep_names = set(getattr(model, "tp_replicated_buckets", ())) if self.tp > 1 else set()
+        self.tp_replicated = [b[0] in rep_names for b in self.flat.buckets]
+        self.sumsq_rep = torch.zeros((), dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self.coef = torch.ones((), dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros((), dtype=torch.float32, device=dev)
@@ -214,8 +221,18 @@ class ZeroEngine:
             if self.use_streams:
                 torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
                 self.rs_event = [None] * nb
+            first, first_rep = True, True
             for i in range(nb):
-                self.k.sumsq(self._grad_seg(i), self.sumsq, accumulate=(i > 0))
+                if self.tp_replicated[i]:
+                    self.k.sumsq(self._grad_seg(i), self.sumsq_rep, accumulate=not first_rep)
+                    first_rep = False
+                else:
+                    self.k.sumsq(self._grad_seg(i), self.sumsq, accumulate=not first)
+                    first = False
+            if self.tp > 1:
+                if not first_rep:
+                    self.sumsq.add_(self.sumsq_rep, alpha=1.0 / self.tp)
+                dist.all_reduce(self.sumsq, op=dist.ReduceOp.SUM, group=self.tp_group)
             if self.world > 1:
                 if self.fsb_comm is not None:
                     self.fsb_comm.all_reduce(self.sumsq)

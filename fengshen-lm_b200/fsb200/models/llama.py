@@ -38,12 +38,21 @@ def _init_normal_(t, std, gen):
 
 
 class LlamaForCausalLM(nn.Module):
-    def __init__(self, config, device=None, world_size=None, seed=0):
+    def __init__(self, config, device=None, world_size=None, seed=0, tp_group=None):
+        """tp_group: the tensor-model-parallel process group (mpu.get_model_parallel_group()) or None. With t = its size > 1
+        this rank holds the shard the reference's `part_{rank}` checkpoints hold (utils/llama_convert/convert_fs_llama_tp.py
+        :143-181): heads / ff columns / vocabulary rows split t ways (ColumnParallelLinear mpu/layers.py:261-360 for QKV,
+        w1, w3 and the LM head; RowParallelLinear :363-470 for dense and w2; VocabParallelEmbedding :62-130), norms replicated.
+        `world_size` is then the DATA-parallel size (ranks that share a tensor-parallel rank)."""
         super().__init__()
         self.config = config
+        import torch.distributed as dist
+        self.tp_group = tp_group
+        self.tp = dist.get_world_size(tp_group) if tp_group is not None else 1
+        self.tp_rank = dist.get_rank(tp_group) if tp_group is not None else 0
         if world_size is None:  # laid out for the job's data-parallel world (the scripts build the model in setup())
-            import torch.distributed as dist
             world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+            world_size //= self.tp
         dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}"
                            if torch.cuda.is_available() else "cuda")
         if dev.type != "cuda":
@@ -57,20 +66,27 @@ class LlamaForCausalLM(nn.Module):
             raise RuntimeError(f"fsb200: head dim {self.hn} unsupported (64 or 128)")
         if V % 8 or h % 8:
             raise RuntimeError("fsb200: vocab_size and hidden_size must be multiples of 8")
+        t = self.tp
+        if nh % t or self.ff % (8 * t) or V % (8 * t):
+            raise RuntimeError(f"fsb200: heads {nh}, ff {self.ff} and vocab {V} must split evenly over tensor-parallel size {t}")
+        # local (per tensor-parallel rank) extents
+        self.nh_l, self.ff_l, self.V_l = nh // t, self.ff // t, V // t
+        self.h_l = self.nh_l * self.hn
+        self.tp_replicated_buckets = ("no_decay",)   # norms: identical on every tensor-parallel rank (counted once in the norm)
 
         spec = FlatSpec()
-        spec.add("llama.embed_in.word_embeddings.weight", (V, h), "embed_in")
+        spec.add("llama.embed_in.word_embeddings.weight", (self.V_l, h), "embed_in")
         for i in range(nl):
             p, bk = f"llama.layers.{i}.", f"layer{i}"
             spec.add(p + "input_layernorm.scale", (h,), bk)          # *.scale names match 'layernorm.' -> no-decay bucket
-            spec.add(p + "attention.query_key_value.weight", (3 * h, h), bk)
-            spec.add(p + "attention.dense.weight", (h, h), bk)
+            spec.add(p + "attention.query_key_value.weight", (3 * self.h_l, h), bk)
+            spec.add(p + "attention.dense.weight", (h, self.h_l), bk)
             spec.add(p + "post_attention_layernorm.scale", (h,), bk)
-            spec.add(p + "mlp.w1.weight", (self.ff, h), bk)   # w1 | w3 adjacent: one [2ff, h] GEMM operand
-            spec.add(p + "mlp.w3.weight", (self.ff, h), bk)
-            spec.add(p + "mlp.w2.weight", (h, self.ff), bk)
+            spec.add(p + "mlp.w1.weight", (self.ff_l, h), bk)   # w1 | w3 adjacent: one [2ff, h] GEMM operand
+            spec.add(p + "mlp.w3.weight", (self.ff_l, h), bk)
+            spec.add(p + "mlp.w2.weight", (h, self.ff_l), bk)
         spec.add("llama.final_layer_norm.scale", (h,), "head")
-        spec.add("embed_out.final_linear.weight", (V, h), "head")
+        spec.add("embed_out.final_linear.weight", (self.V_l, h), "head")
         self.flat = FlatBuffers(spec, dev, world_size=world_size)
 
         # module tree mirroring the reference (modeling_llama.py:97-127, :239-252)
@@ -110,9 +126,9 @@ class LlamaForCausalLM(nn.Module):
         self.embed_out.final_linear = _Holder()
         self.embed_out.final_linear.weight = P("embed_out.final_linear.weight")
 
-        self._w13 = [self.flat.span(f"llama.layers.{i}.mlp.w1.weight", 2 * self.ff, h)
+        self._w13 = [self.flat.span(f"llama.layers.{i}.mlp.w1.weight", 2 * self.ff_l, h)
                      for i in range(nl)]
-        self._dw13 = [self.flat.span(f"llama.layers.{i}.mlp.w1.weight", 2 * self.ff, h, grad=True) for i in range(nl)]
+        self._dw13 = [self.flat.span(f"llama.layers.{i}.mlp.w1.weight", 2 * self.ff_l, h, grad=True) for i in range(nl)]
 
         # RoPE tables exactly as RotaryEmbedding builds them (layers/positional_embeddings.py:38-52), fp32
         self._inv_freq = inv_freq
@@ -143,7 +159,7 @@ class LlamaForCausalLM(nn.Module):
         small = math.sqrt(2.0 / (5.0 * h))
         wang = 2.0 / (nl * math.sqrt(h))
         big = self.flat.total > 300_000_000  # billions of CPU randn take minutes: draw on the device instead
-        gen = torch.Generator(device=self.flat.params.device if big else "cpu").manual_seed(seed)
+        gen = torch.Generator(device=self.flat.params.device if big else "cpu").manual_seed(seed + 7919 * self.tp_rank)
         for name, prm in self.named_parameters():
             if name.endswith(".scale"):
                 prm.fill_(1.0)
@@ -214,33 +230,41 @@ class LlamaForCausalLM(nn.Module):
                                past_key_values=None, hidden_states=None, attentions=None)
 
     def _forward_impl(self, ids, pos, lab, B, S, save, want_logits):
-        h, nh, hn, ff = self.h, self.nh, self.hn, self.ff
+        h, nh, hn, ff = self.h, self.nh_l, self.hn, self.ff_l          # LOCAL heads / ff columns under tensor parallelism
+        hl = self.h_l
         T = B * S
         acts = []
         self._need("no_decay"); self._need("embed_in")
-        x = ops.embedding_fwd(ids, self.llama.embed_in.word_embeddings.weight.data)
+        ids_l, emb_keep = self._local_ids(ids)
+        x = ops.embedding_fwd(ids_l, self.llama.embed_in.word_embeddings.weight.data)
+        if emb_keep is not None:      # VocabParallelEmbedding.forward (mpu/layers.py:104-130): foreign rows are zero, then all-reduce
+            x.mul_(emb_keep)
+            self._tp_all_reduce(x)
         prev_m = None
         for i, lyr in enumerate(self.llama.layers):
             self._need(f"layer{i}")
             h1, rstd1, x = ops.rmsnorm_fwd(x if prev_m is None else prev_m, lyr.input_layernorm.scale.data, self.eps,
                                            residual=None if prev_m is None else x)
             qkv = ops.gemm(L.GEMM_NT, h1, lyr.attention.query_key_value.weight.data)
-            ops.rope_inplace(qkv, self._cos, self._sin, pos, nh, hn, 3 * h, 3 * hn, offset=0)
-            ops.rope_inplace(qkv, self._cos, self._sin, pos, nh, hn, 3 * h, 3 * hn, offset=hn)
+            ops.rope_inplace(qkv, self._cos, self._sin, pos, nh, hn, 3 * hl, 3 * hn, offset=0)
+            ops.rope_inplace(qkv, self._cos, self._sin, pos, nh, hn, 3 * hl, 3 * hn, offset=hn)
             q5 = qkv.view(B, S, nh, 3, hn)
             o, lse = ops.sdpa_fwd(q5[:, :, :, 0], q5[:, :, :, 1], q5[:, :, :, 2], 1.0 / math.sqrt(hn), True)
-            o2 = o.view(T, h)
+            o2 = o.view(T, hl)
             a = ops.gemm(L.GEMM_NT, o2, lyr.attention.dense.weight.data)
+            self._tp_all_reduce(a)        # RowParallelLinear: partial sums over the head shards (mpu/layers.py:451-470)
             h2, rstd2, x1 = ops.rmsnorm_fwd(a, lyr.post_attention_layernorm.scale.data, self.eps, residual=x)
             gu = ops.gemm(L.GEMM_NT, h2, self._w13[i])
             act = ops.glu_fwd(L.ACT_SILU, gu[:, :ff], gu[:, ff:])
             m = ops.gemm(L.GEMM_NT, act, lyr.mlp.w2.weight.data)
+            self._tp_all_reduce(m)        # RowParallelLinear (w2)
             if save:
                 acts.append((x, rstd1, h1, qkv, o, lse, x1, rstd2, h2, gu, act))
             x, prev_m = x1, m
         self._need("head")
         hf, rstdf, xf = ops.rmsnorm_fwd(prev_m, self.llama.final_layer_norm.scale.data, self.eps, residual=x)
         logits = ops.gemm(L.GEMM_NT, hf, self.embed_out.final_linear.weight.data)
+        logits = self._tp_gather_columns(logits)   # ParallelLinear(parallel_output=False): full-vocabulary logits on every rank
         loss = None
         ctx = None
         if lab is not None:
@@ -265,6 +289,8 @@ class LlamaForCausalLM(nn.Module):
 
     def _layer_infer(self, i, x, prev_m, pos, B, S, kc, vc, at, kv_mask, causal):
         """One layer forward without saving activations; writes this call's keys / values into the cache at [at, at + S)."""
+        if self.tp > 1:
+            raise NotImplementedError("fsb200: KV-cache decoding under tensor parallelism is not implemented")
         h, nh, hn, ff = self.h, self.nh, self.hn, self.ff
         lyr = self.llama.layers[i]
         h1, _, x = ops.rmsnorm_fwd(x if prev_m is None else prev_m, lyr.input_layernorm.scale.data, self.eps,
@@ -375,14 +401,18 @@ class LlamaForCausalLM(nn.Module):
     # ---- backward ---------------------------------------------------------------------------------------------------
     def _backward_impl(self, ctx, gloss):
         acts, hf, rstdf, xf, dlogits, ids, pos, B, S = ctx
-        h, nh, hn, ff = self.h, self.nh, self.hn, self.ff
+        h, nh, hn, ff = self.h, self.nh_l, self.hn, self.ff_l
+        hl = self.h_l
         T = B * S
         acc = self.accumulate_grads
         self._begin_backward()
         if gloss is not None:
             ops.scale_inplace(dlogits, gloss)  # upstream scalar; the kernel exits immediately when it is 1.0
+        if self.tp > 1:   # this rank's vocabulary columns of dlogits (a strided view: the GEMMs take the row stride)
+            dlogits = dlogits[:, self.tp_rank * self.V_l:(self.tp_rank + 1) * self.V_l]
         W_out = self.embed_out.final_linear.weight
         dhf = ops.gemm(L.GEMM_NN, dlogits, W_out.data)
+        self._tp_all_reduce(dhf)          # backward of copy_to_model_parallel_region (mpu/mappings.py): sum the partial dgrads
         ops.gemm(L.GEMM_TN, dlogits, hf, out=W_out.main_grad, accumulate=acc)
         del dlogits
         self._done("head")
@@ -399,21 +429,23 @@ class LlamaForCausalLM(nn.Module):
             dgu = torch.empty_like(gu)
             ops.glu_bwd(L.ACT_SILU, dact, gu[:, :ff], gu[:, ff:], dgu[:, :ff], dgu[:, ff:])
             dh2 = ops.gemm(L.GEMM_NN, dgu, self._w13[i])
+            self._tp_all_reduce(dh2)      # column-parallel w1|w3: dgrad partial sums
             ops.gemm(L.GEMM_TN, dgu, h2, out=self._dw13[i], accumulate=acc)
             s2 = lyr.post_attention_layernorm.scale
             dx1 = ops.rmsnorm_bwd(dh2, x1, s2.data, rstd2, s2.main_grad, accumulate=acc, dres=dx)
             # x1 = x + a  ->  da = dx1
             wd = lyr.attention.dense.weight
             do = ops.gemm(L.GEMM_NN, dx1, wd.data)
-            ops.gemm(L.GEMM_TN, dx1, o.view(T, h), out=wd.main_grad, accumulate=acc)
+            ops.gemm(L.GEMM_TN, dx1, o.view(T, hl), out=wd.main_grad, accumulate=acc)
             dqkv = torch.empty_like(qkv)
             q5, d5 = qkv.view(B, S, nh, 3, hn), dqkv.view(B, S, nh, 3, hn)
             ops.sdpa_bwd(q5[:, :, :, 0], q5[:, :, :, 1], q5[:, :, :, 2], o, do.view(B, S, nh, hn), lse,
                          1.0 / math.sqrt(hn), True, d5[:, :, :, 0], d5[:, :, :, 1], d5[:, :, :, 2])
-            ops.rope_inplace(dqkv, self._cos, self._sin, pos, nh, hn, 3 * h, 3 * hn, backward=True, offset=0)
-            ops.rope_inplace(dqkv, self._cos, self._sin, pos, nh, hn, 3 * h, 3 * hn, backward=True, offset=hn)
+            ops.rope_inplace(dqkv, self._cos, self._sin, pos, nh, hn, 3 * hl, 3 * hn, backward=True, offset=0)
+            ops.rope_inplace(dqkv, self._cos, self._sin, pos, nh, hn, 3 * hl, 3 * hn, backward=True, offset=hn)
             wq = lyr.attention.query_key_value.weight
             dh1 = ops.gemm(L.GEMM_NN, dqkv, wq.data)
+            self._tp_all_reduce(dh1)      # column-parallel QKV: dgrad partial sums
             ops.gemm(L.GEMM_TN, dqkv, h1, out=wq.main_grad, accumulate=acc)
             s1 = lyr.input_layernorm.scale
             dx = ops.rmsnorm_bwd(dh1, x, s1.data, rstd1, s1.main_grad, accumulate=acc, dres=dx1)
@@ -421,9 +453,36 @@ class LlamaForCausalLM(nn.Module):
         W_in = self.llama.embed_in.word_embeddings.weight
         if not acc:
             W_in.main_grad.zero_()
-        ops.embedding_bwd(ids, dx, W_in.main_grad)
+        ids_l, emb_keep = self._local_ids(ids)
+        if emb_keep is not None:
+            dx = dx * emb_keep            # rows of foreign vocabulary shards contribute nothing here
+        ops.embedding_bwd(ids_l, dx, W_in.main_grad)
         self._done("embed_in")
         self._done("no_decay")
+
+    # ---- tensor-parallel exchanges (fengshen/models/megatron/mpu/mappings.py:29-192), NCCL on the compute stream -------------
+    def _tp_all_reduce(self, t):
+        if self.tp > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, group=self.tp_group)
+
+    def _tp_gather_columns(self, t):
+        """[rows, n/tp] on every rank -> [rows, n] (gather_from_model_parallel_region, last-dimension concatenation)."""
+        if self.tp == 1:
+            return t
+        import torch.distributed as dist
+        buf = torch.empty((self.tp,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(buf, t.contiguous(), group=self.tp_group)
+        return buf.permute(1, 0, 2).reshape(t.shape[0], self.tp * t.shape[1])
+
+    def _local_ids(self, ids):
+        """VocabParallelEmbedding index arithmetic (mpu/layers.py:104-121): ids of this rank's vocabulary range re-based to 0,
+        foreign ids clamped (their rows are zeroed by the returned [rows, 1] bf16 mask). (ids, None) without tensor parallelism."""
+        if self.tp == 1:
+            return ids, None
+        lo = self.tp_rank * self.V_l
+        mine = (ids >= lo) & (ids < lo + self.V_l)
+        return torch.where(mine, ids - lo, torch.zeros_like(ids)), mine.to(torch.bfloat16)[:, None]
 
     def _done(self, bucket):
         if self.grad_hook is not None:

@@ -87,12 +87,12 @@ def rotate_half(x):
     return torch.cat((-x2, x1), dim=-1)
 
 
-def attention(x, wqkv, wd, pos, nh, cos, sin):
+def attention(x, wqkv, wd, pos, nh, cos, sin, hn=None):
     """ParallelSelfAttention.forward, layers/transformer.py:476-568 with the `global` core (:307-408):
     per-head interleaved QKV split (:488-497), rotary on q,k gathered by position_ids
     (positional_embeddings.py:78-87), scores = q k^T / sqrt(hn) (:338-344), causal masked softmax, context, dense."""
     B, S, h = x.shape
-    hn = h // nh
+    hn = h // nh if hn is None else hn      # hn given: a tensor-parallel shard (nh = LOCAL heads, wd = [h, nh * hn] row-parallel slice)
     mixed = F.linear(x, wqkv).view(B, S, nh, 3 * hn)
     q, k, v = mixed[..., :hn], mixed[..., hn:2 * hn], mixed[..., 2 * hn:]
     c = cos[pos].to(x.dtype)[:, :, None, :]  # [B,S,1,hn]
@@ -103,7 +103,7 @@ def attention(x, wqkv, wd, pos, nh, cos, sin):
     causal = torch.triu(torch.ones(S, S, dtype=torch.bool), diagonal=1)
     scores = scores.masked_fill(causal, torch.finfo(scores.dtype).min)  # modeling_llama.py:71-74
     probs = torch.softmax(scores, dim=-1)
-    ctx = torch.einsum("bhqk,bkhd->bqhd", probs, v).reshape(B, S, h)
+    ctx = torch.einsum("bhqk,bkhd->bqhd", probs, v).reshape(B, S, nh * hn)
     return F.linear(ctx, wd)
 
 

@@ -119,8 +119,9 @@ def test_strategy_reads_deepspeed_json_from_env(tmp_path, monkeypatch):
     s = DeepSpeedStrategy(tensor_model_parallel_size=1, pipe_model_parallel_size=1, mpu_seed=42)
     assert s.stage == 2 and s.gradient_clipping == 1.0 and s.precision == "bf16"
     assert "offload_optimizer" not in s.config["zero_optimization"]
-    with pytest.raises(NotImplementedError):
-        DeepSpeedStrategy(tensor_model_parallel_size=8, pipe_model_parallel_size=1, mpu_seed=42)
+    assert DeepSpeedStrategy(tensor_model_parallel_size=8, pipe_model_parallel_size=1, mpu_seed=42).tensor_model_parallel_size == 8
+    with pytest.raises(NotImplementedError):   # pipeline parallelism stays outside the hot path
+        DeepSpeedStrategy(tensor_model_parallel_size=1, pipe_model_parallel_size=2, mpu_seed=42)
     monkeypatch.setenv("PL_DEEPSPEED_CONFIG_PATH", str(tmp_path / "missing.json"))
     with pytest.raises(FileNotFoundError):
         DeepSpeedStrategy(tensor_model_parallel_size=1, pipe_model_parallel_size=1, mpu_seed=42)
@@ -174,3 +175,38 @@ def test_llama_hf_fs_converters_roundtrip_and_match_transformers():
     want, _ = O.forward(fs, batch, nh)
     got = hf(input_ids=batch["input_ids"], labels=batch["labels"]).loss
     assert abs(got.item() - want.item()) < 2e-5, (got.item(), want.item())
+
+
+def test_tp_shard_layout_matches_reference_and_sharded_math_equals_full():
+    """convert_fs_llama_tp.py:143-181 shard format + the column / row-parallel algebra of mpu/layers.py: running every shard's
+    slice of the layer and summing the row-parallel partial outputs reproduces the un-sharded oracle layer exactly (fp32)."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import math
+    import llama_oracle as O
+    import torch.nn.functional as F
+    from fengshen.utils.llama_convert import merge_state_dict_tp, split_state_dict_tp
+    V, h, L, nh, S, tp = 64, 128, 1, 4, 12, 2
+    hn = h // nh
+    sd = O.make_weights(V, h, L, seed=1, bf16_exact=False)
+    shards = split_state_dict_tp(sd, tp, nh)
+    assert shards[0]["llama.layers.0.attention.query_key_value.weight"].shape == (3 * h // tp, h)
+    assert shards[1]["llama.layers.0.attention.dense.weight"].shape == (h, h // tp)
+    assert shards[0]["llama.layers.0.mlp.w2.weight"].shape[1] * tp == sd["llama.layers.0.mlp.w2.weight"].shape[1]
+    assert shards[1]["llama.embed_in.word_embeddings.weight"].shape == (V // tp, h)
+    merged = merge_state_dict_tp(shards, nh)
+    assert all(torch.equal(merged[k], sd[k]) for k in sd)
+    # sharded attention + MLP == full (the all-reduce is the sum over shards)
+    batch = O.make_batch(V, 2, S, seed=2)
+    x = F.embedding(batch["input_ids"], sd["llama.embed_in.word_embeddings.weight"])
+    cos, sin = O.rope_tables(hn, 64)
+    p = "llama.layers.0."
+    xin = O.rmsnorm(x, sd[p + "input_layernorm.scale"], 1e-6)
+    full = O.attention(xin, sd[p + "attention.query_key_value.weight"], sd[p + "attention.dense.weight"], batch["position_ids"], nh,
+                       cos, sin)
+    part = sum(O.attention(xin, s_[p + "attention.query_key_value.weight"], s_[p + "attention.dense.weight"], batch["position_ids"],
+                           nh // tp, cos, sin, hn=hn) for s_ in shards)
+    assert torch.allclose(part, full, atol=1e-5)
+    fm = O.mlp(xin, sd[p + "mlp.w1.weight"], sd[p + "mlp.w3.weight"], sd[p + "mlp.w2.weight"])
+    pm = sum(O.mlp(xin, s_[p + "mlp.w1.weight"], s_[p + "mlp.w3.weight"], s_[p + "mlp.w2.weight"]) for s_ in shards)
+    assert torch.allclose(pm, fm, atol=1e-5)
