@@ -43,13 +43,10 @@ def _run(rank, world, port, q):
     full = O.make_weights(V, H, NL, seed=0)
     model = LlamaForCausalLM(_cfg(), device=dev, world_size=1, tp_group=tp_group)
     model.load_reference_state_dict(split_state_dict_tp(full, world, NH)[rank] if world > 1 else full)
-    eng = ZeroEngine(model, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0,
-                     process_group=dist.new_group([rank]) if world > 1 and False else None, tp_group=tp_group) \
-        if world == 1 else None
-    if world > 1:
-        solo = [dist.new_group([r]) for r in range(world)]
-        eng = ZeroEngine(model, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, process_group=solo[rank],
-                         tp_group=tp_group)
+    dp_group = None
+    if world > 1:   # data-parallel size 1: each rank is alone in its data-parallel group (every rank creates every group)
+        dp_group = [dist.new_group([r]) for r in range(world)][rank]
+    eng = ZeroEngine(model, lr=1e-3, betas=(0.9, 0.95), weight_decay=0.1, grad_clip=1.0, process_group=dp_group, tp_group=tp_group)
     losses, g0 = [], None
     for it in range(STEPS):
         ids = O.make_batch(V, 2, S, seed=50 + it)["input_ids"].to(dev)
