@@ -53,12 +53,13 @@ def _run(rank, world, port, q):
         out = model(input_ids=ids, labels=ids)
         out.loss.backward()
         if it == 0:
-            g0 = {n: p.main_grad.float().cpu().clone() for n, p in model.named_parameters()}
+            g0 = {n: p.main_grad.float().cpu().numpy().copy() for n, p in model.named_parameters()}
         eng.backward_done()
         eng.step()
         losses.append(out.loss.item())
     eng.wait_params()
-    q.put((world, rank, losses, g0, {n: p.detach().float().cpu() for n, p in model.named_parameters()},
+    # numpy arrays (pickled by value): torch tensors travel through shared-memory handles that die with the child
+    q.put((world, rank, losses, g0, {n: p.detach().float().cpu().numpy().copy() for n, p in model.named_parameters()},
            float(eng.grad_norm.item())))
     if world > 1:
         dist.barrier()
@@ -86,14 +87,15 @@ def test_tensor_parallel_2_matches_single_gpu():
     for a, b in zip(res[0][2], single[2]):
         assert abs(a - b) < 5e-3, (res[0][2], single[2])
     # first-step gradients: every shard gradient is the matching slice of the full gradient
-    full_g = single[3]
-    merged_g = merge_state_dict_tp([res[0][3], res[1][3]], NH)
+    T = lambda d: {k: torch.from_numpy(v) for k, v in d.items()}
+    full_g = T(single[3])
+    merged_g = merge_state_dict_tp([T(res[0][3]), T(res[1][3])], NH)
     for name, want in full_g.items():
         got = merged_g[name]
         cos = torch.dot(got.flatten(), want.flatten()) / (got.norm() * want.norm() + 1e-30)
         assert cos.item() > 0.999, (name, cos.item())
     # clipped AdamW: same global gradient norm (replicated norms counted once), merged parameters track the single-GPU run
     assert abs(res[0][5] - single[5]) < 2e-2 * single[5], (res[0][5], single[5])
-    merged_p = merge_state_dict_tp([res[0][4], res[1][4]], NH)
-    for name, want in single[4].items():
+    merged_p = merge_state_dict_tp([T(res[0][4]), T(res[1][4])], NH)
+    for name, want in T(single[4]).items():
         assert (merged_p[name] - want).abs().max().item() < 2e-2, name
