@@ -371,7 +371,7 @@ def run_workload(name, args, world, rank, device, pg, steps, warmup, want_e2e=Tr
     total_steps = 1000
     stepper = PretrainStep(model, lambda s_: polynomial_lr(s_, w["lr"], 0.01 * total_steps, total_steps, 1e-7), lr=w["lr"],
                            betas=w["betas"], weight_decay=w["wd"], grad_clip=w["clip"], ga_steps=ga, process_group=pg,
-                           stage=w.get("stage", 2), comm_sms=args.comm_sms)
+                           stage=w.get("stage", 2), comm_sms=args.comm_sms, cuda_graph=bool(args.cuda_graph) and world == 1)
     pool = 2
     host = [make_host_batches(w, ga, rank) for _ in range(pool)]
     dev = [[{k: v.to(device) for k, v in b.items()} for b in hb] for hb in host]
@@ -396,6 +396,8 @@ def run_workload(name, args, world, rank, device, pg, steps, warmup, want_e2e=Tr
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
 
     gsum, prof_ms = {"launches": 0, "ms": 0.0, "work": 0.0}, 0.0
+    if stepper.cuda_graph:        # the per-GEMM events of the roofline block need eager launches
+        stepper.cuda_graph = False
     if profile_steps:
         prof = ops.KernelProfiler()
         ops.set_profiler(prof)
@@ -533,6 +535,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the cross-rank parity block at --gpus > 1")
     ap.add_argument("--comm-sms", type=int, default=int(os.environ.get("FSB_COMM_SMS", "0")),
                     help="SMs the persistent GEMM grids leave to overlapping NCCL kernels (multi-GPU only)")
+    ap.add_argument("--cuda-graph", type=int, default=0,
+                    help="1: capture the whole optimizer step in a CUDA graph and replay it (single GPU; launch-bound configs)")
     ap.add_argument("--breakdown", action="store_true",
                     help="after the timed runs, profile 2 more steps with CUDA events around every fsb_* call and print the "
                          "per-entry-point time table to stderr (diagnostic; not part of the JSON line)")

@@ -144,9 +144,13 @@ struct AdamArgs {
 template <bool kGradF32>
 __global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v,
                                                     const void* __restrict__ g_, __nv_bfloat16* __restrict__ p16,
-                                                    int64_t n, AdamArgs a, const float* __restrict__ grad_scale) {
+                                                    int64_t n, AdamArgs a, const float* __restrict__ grad_scale,
+                                                    const float* __restrict__ hyper) {
   const float gs = grad_scale ? *grad_scale : 1.f;
   const int64_t nvec = n >> 2;
+  if (hyper != nullptr) {   // per-step scalars from DEVICE memory: the launch is then identical every step (CUDA-graph replay)
+    a.lr = hyper[0]; a.bc1 = hyper[1]; a.bc2_sqrt = hyper[2];
+  }
   const float step = a.lr / a.bc1;
   const float decay = 1.f - a.lr * a.weight_decay;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < nvec; i += int64_t(gridDim.x) * blockDim.x) {
@@ -262,8 +266,10 @@ extern "C" int fsb_softmax_xent_fwd_bwd(const void* logits, const int64_t* label
 
 extern "C" int fsb_adamw_flat(float* master, float* exp_avg, float* exp_avg_sq, const void* grad, int grad_dtype,
                               void* param16, int64_t n, float lr, float beta1, float beta2, float eps,
-                              float weight_decay, int64_t step, const float* grad_scale, fsb_stream_t st) {
-  FSB_REQUIRE(master && exp_avg && exp_avg_sq && grad && n > 0 && step >= 1, "adamw: bad args");
+                              float weight_decay, int64_t step, const float* grad_scale, const float* hyper,
+                              fsb_stream_t st) {
+  FSB_REQUIRE(master && exp_avg && exp_avg_sq && grad && n > 0 && (step >= 1 || hyper != nullptr), "adamw: bad args");
+  if (step < 1) step = 1;   // placeholder when the device scalars carry the bias corrections
   FSB_REQUIRE(n % 4 == 0, "adamw: n=%ld must be a multiple of 4 (pad the flat shard)", (long)n);
   FSB_REQUIRE(aligned16(master) && aligned16(exp_avg) && aligned16(exp_avg_sq) &&
                   (reinterpret_cast<uintptr_t>(grad) & 7) == 0 && (reinterpret_cast<uintptr_t>(param16) & 7) == 0,
@@ -277,10 +283,10 @@ extern "C" int fsb_adamw_flat(float* master, float* exp_avg, float* exp_avg_sq, 
   const int g = int(blocks < cap ? blocks : cap);
   if (grad_dtype == FSB_F32)
     adamw_kernel<true><<<g, 256, 0, (cudaStream_t)st>>>(master, exp_avg, exp_avg_sq, grad, (__nv_bfloat16*)param16, n, a,
-                                                        grad_scale);
+                                                        grad_scale, hyper);
   else
     adamw_kernel<false><<<g, 256, 0, (cudaStream_t)st>>>(master, exp_avg, exp_avg_sq, grad, (__nv_bfloat16*)param16, n, a,
-                                                         grad_scale);
+                                                         grad_scale, hyper);
   FSB_CUDA_LAUNCH_CHECK();
   return FSB_OK;
 }

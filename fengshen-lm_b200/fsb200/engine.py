@@ -68,6 +68,9 @@ class ZeroEngine:
         self.sumsq = torch.zeros((), dtype=torch.float32, device=dev)
         self.coef = torch.ones((), dtype=torch.float32, device=dev)
         self.grad_norm = torch.zeros((), dtype=torch.float32, device=dev)
+        # per-step scalars of AdamW in device memory (CUDA-graph mode: see set_device_hyper / trainer.PretrainStep)
+        self.hyper = None
+        self._hyper_host = None
         self.use_streams = dev.type == "cuda" and overlap_comm and self.world > 1
         self.comm_stream = torch.cuda.Stream(device=dev) if self.use_streams else None
         # ZeRO-2: per-layer gradients live in rotating slots whenever they are consumed bucket by bucket (reduced or
@@ -210,6 +213,19 @@ class ZeroEngine:
             self.rs_event[i] = None
 
     # ---- optimizer step ----------------------------------------------------------------------------------------
+    def enable_device_hyper(self):
+        """Keep {lr, 1 - beta1^t, sqrt(1 - beta2^t)} in a device tensor that AdamW reads: every step then issues byte-identical
+        launches, so the whole step can be captured in a CUDA graph. Call set_device_hyper(lr) before each (replayed) step."""
+        self.hyper = torch.zeros(3, dtype=torch.float32, device=self.device)
+        self._hyper_host = torch.zeros(3, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else torch.zeros(3)
+
+    def set_device_hyper(self, lr, step=None):
+        step = (self.step_count + 1) if step is None else step
+        self._hyper_host[0] = float(lr)
+        self._hyper_host[1] = 1.0 - self.betas[0] ** step
+        self._hyper_host[2] = (1.0 - self.betas[1] ** step) ** 0.5
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
+
     def step(self, lr=None, weight_decay=None):
         if self.micro != self.ga_steps:
             raise RuntimeError(f"ZeroEngine.step() after {self.micro} micro-batches, expected {self.ga_steps}")
@@ -248,7 +264,8 @@ class ZeroEngine:
                 self._wait_rs(i)
             self.k.adamw_flat(self._seg(self.master, i), self._seg(self.exp_avg, i), self._seg(self.exp_avg_sq, i),
                               self._grad_seg(i), self.flat.bucket_slice(i, self.rank), lr, self.betas[0], self.betas[1],
-                              self.eps, wd if decay_on else 0.0, self.step_count, coef)
+                              self.eps, wd if decay_on else 0.0, self.step_count, coef,
+                              **({"hyper": self.hyper} if self.hyper is not None else {}))
             if self.world > 1:
                 if self.use_streams:
                     self.comm_stream.wait_stream(cur)

@@ -63,7 +63,7 @@ SIGNATURES = {
     "fsb_softmax_xent_fwd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64,
                                          c_i64, c_i64, c_int, c_int, c_f32, c_void_p]),
     "fsb_adamw_flat": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_i64, c_f32, c_f32, c_f32,
-                               c_f32, c_f32, c_i64, c_void_p, c_void_p]),
+                               c_f32, c_f32, c_i64, c_void_p, c_void_p, c_void_p]),
     "fsb_sumsq_workspace_bytes": (c_size, []),
     "fsb_sumsq": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_int, c_void_p, c_size, c_void_p]),
     "fsb_clip_coef": (c_int, [c_void_p, c_f32, c_void_p, c_void_p, c_void_p]),

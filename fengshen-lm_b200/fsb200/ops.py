@@ -301,10 +301,11 @@ def softmax_xent(logits, labels, seq_len, shift=1, ignore_index=-100, grad_scale
     return loss, dl, n_valid
 
 
-def adamw_flat(master, m, v, grad, param16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None):
+def adamw_flat(master, m, v, grad, param16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None, hyper=None):
+    """hyper: optional fp32 CUDA tensor [lr, 1 - beta1^t, sqrt(1 - beta2^t)] read by the kernel instead of lr / step."""
     L.call("fsb_adamw_flat", _p(master), _p(m), _p(v), _p(grad), L.F32 if grad.dtype == torch.float32 else L.BF16,
            _p(param16), master.numel(), float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
-           _p(grad_scale), _stream())
+           _p(grad_scale), _p(hyper), _stream())
 
 
 def sumsq(x, out, accumulate=False):

@@ -171,10 +171,13 @@ int fsb_softmax_xent_fwd_bwd(const void* logits, const int64_t* labels, void* dl
  * deepspeed.ops.adam.FusedAdam(adam_w_mode=True) as selected at fengshen/models/model_utils.py:69-72, in
  * torch.optim.AdamW's operation order, on the rank's flat fp32 shard {master, exp_avg, exp_avg_sq}; grad bf16 or fp32;
  * param16 (bf16, may be NULL) receives the updated parameters. grad_scale: optional DEVICE scalar multiplied into the
- * gradient (clip coefficient). n % 4 == 0. fsb_sumsq / fsb_clip_coef give torch.nn.utils.clip_grad_norm_ semantics. */
+ * gradient (clip coefficient). n % 4 == 0. fsb_sumsq / fsb_clip_coef give torch.nn.utils.clip_grad_norm_ semantics.
+ * hyper: optional DEVICE array {lr, 1 - beta1^t, sqrt(1 - beta2^t)} that overrides `lr` / `step` — the per-step scalars then
+ * live in device memory and the launch is byte-identical every step, which is what lets a whole training step be captured
+ * in a CUDA graph and replayed (fsb200.trainer.PretrainStep(cuda_graph=True)). */
 int fsb_adamw_flat(float* master, float* exp_avg, float* exp_avg_sq, const void* grad, int grad_dtype, void* param16,
                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
-                   const float* grad_scale, fsb_stream_t stream);
+                   const float* grad_scale, const float* hyper, fsb_stream_t stream);
 size_t fsb_sumsq_workspace_bytes(void);
 int fsb_sumsq(const void* x, int dtype, int64_t n, float* out, int accumulate, void* workspace, size_t workspace_bytes,
               fsb_stream_t stream);

@@ -26,7 +26,7 @@ def clip_coef(sumsq_t, max_norm, coef_out, norm_out=None):
     coef_out.copy_(torch.clamp(c, max=1.0) if max_norm > 0 else torch.ones_like(c))
 
 
-def adamw_flat(master, m, v, grad, param16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None):
+def adamw_flat(master, m, v, grad, param16, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None, hyper=None):
     g = grad.float() * (grad_scale if grad_scale is not None else 1.0)
     master.mul_(1 - lr * weight_decay)
     m.mul_(beta1).add_(g, alpha=1 - beta1)
