@@ -45,7 +45,7 @@ WORKLOADS = {
     # Randeng-T5-784M = mT5-large shape: d 1024, 24+24 layers, 16 heads x 64, gated-GeLU d_ff 2816; the
     # released vocabulary (32598, pretrain_t5.py:90) padded to a multiple of 8; enc / dec 512 as BASELINE words it
     "randeng-t5-784m": dict(family="t5", vocab_size=32600, d_model=1024, d_kv=64, d_ff=2816, num_layers=24, num_heads=16,
-                            seq=512, seq_dec=512, per_gpu=32, micro=16, lr=1e-4, betas=(0.9, 0.999), wd=0.1, clip=1.0,
+                            seq=512, seq_dec=512, per_gpu=32, micro=32, lr=1e-4, betas=(0.9, 0.999), wd=0.1, clip=1.0,
                             label="Randeng-T5-784M seq2seq pretrain, enc 512 / dec 512, batch 32/GPU, ZeRO-2 (BASELINE configs[4])"),
     "ziya-llama-13b": dict(family="llama", vocab_size=39424, hidden_size=5120, num_hidden_layers=40,
                            num_attention_heads=40, seq=2048, per_gpu=32, micro=4, lr=1e-4, betas=(0.9, 0.95), wd=0.1,
@@ -537,6 +537,7 @@ def main():
                     help="SMs the persistent GEMM grids leave to overlapping NCCL kernels (multi-GPU only)")
     ap.add_argument("--cuda-graph", type=int, default=0,
                     help="1: capture the whole optimizer step in a CUDA graph and replay it (single GPU; launch-bound configs)")
+    ap.add_argument("--no-graph-block", action="store_true", help="skip the extra CUDA-graph measurement at --gpus 1")
     ap.add_argument("--breakdown", action="store_true",
                     help="after the timed runs, profile 2 more steps with CUDA events around every fsb_* call and print the "
                          "per-entry-point time table to stderr (diagnostic; not part of the JSON line)")
@@ -590,6 +591,17 @@ def main():
     warm = max(3, args.warmup)
     main_run = run_workload(args.workload, args, world, rank, device, pg, args.steps, warm, want_e2e=not args.no_e2e,
                             overrides=over)
+    graph_block = None
+    if world == 1 and not args.cuda_graph and not args.no_graph_block:
+        # the same workload with the whole optimizer step captured in ONE CUDA graph and replayed (bit-identical results,
+        # tests/test_llama_gpu.py::test_cuda_graph_step_equals_eager_step). Reported beside `value`, which stays on eager
+        # launches so that the N = 1 and N > 1 lines of the scaling run measure the same code path.
+        args.cuda_graph = 1
+        gr = run_workload(args.workload, args, world, rank, device, pg, args.steps, warm, want_e2e=False, profile_steps=0,
+                          overrides=over)
+        args.cuda_graph = 0
+        graph_block = {"tokens_per_s": gr["value"], "ms_per_step": gr["ms_per_step"], "steps": args.steps,
+                       "gpu_launches_replayed": gr["launches"], "speedup_vs_eager": gr["value"] / main_run["value"]}
     parity = None
     if world > 1 and not args.no_parity:
         parity = parity_block(world, rank, device)
@@ -621,6 +633,8 @@ def main():
             "roofline": main_run["roofline"], "e2e": main_run["e2e"], "gpu_launches": main_run["launches"],
             "clocks": main_run["clocks"], "final_loss": main_run["final_loss"], "memory_bytes": main_run["memory"],
             "comm_bytes_per_step_per_gpu": main_run["comm_bytes_per_step_per_gpu"]}
+    if graph_block is not None:
+        line["cuda_graph_step"] = graph_block
     if parity is not None:
         line["parity"] = parity
     if headline is not None:

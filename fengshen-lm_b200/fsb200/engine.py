@@ -70,7 +70,6 @@ class ZeroEngine:
         self.grad_norm = torch.zeros((), dtype=torch.float32, device=dev)
         # per-step scalars of AdamW in device memory (CUDA-graph mode: see set_device_hyper / trainer.PretrainStep)
         self.hyper = None
-        self._hyper_host = None
         self.use_streams = dev.type == "cuda" and overlap_comm and self.world > 1
         self.comm_stream = torch.cuda.Stream(device=dev) if self.use_streams else None
         # ZeRO-2: per-layer gradients live in rotating slots whenever they are consumed bucket by bucket (reduced or
@@ -217,14 +216,16 @@ class ZeroEngine:
         """Keep {lr, 1 - beta1^t, sqrt(1 - beta2^t)} in a device tensor that AdamW reads: every step then issues byte-identical
         launches, so the whole step can be captured in a CUDA graph. Call set_device_hyper(lr) before each (replayed) step."""
         self.hyper = torch.zeros(3, dtype=torch.float32, device=self.device)
-        self._hyper_host = torch.zeros(3, dtype=torch.float32).pin_memory() if self.device.type == "cuda" else torch.zeros(3)
 
     def set_device_hyper(self, lr, step=None):
         step = (self.step_count + 1) if step is None else step
-        self._hyper_host[0] = float(lr)
-        self._hyper_host[1] = 1.0 - self.betas[0] ** step
-        self._hyper_host[2] = (1.0 - self.betas[1] ** step) ** 0.5
-        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        # a fresh PAGEABLE host tensor per call: cudaMemcpyAsync stages pageable memory before it returns, so the host may run
+        # many steps ahead of the device without a later step's scalars overtaking an earlier step's copy
+        # the C side receives beta1 / beta2 as C floats and forms the corrections in double from THOSE values: do the same, so
+        # that a replayed step is bit-identical to the eager one
+        b1, b2 = (float(torch.tensor(x, dtype=torch.float32)) for x in self.betas)
+        host = torch.tensor([float(lr), 1.0 - b1 ** step, (1.0 - b2 ** step) ** 0.5], dtype=torch.float32)
+        self.hyper.copy_(host, non_blocking=True)
 
     def step(self, lr=None, weight_decay=None):
         if self.micro != self.ga_steps:

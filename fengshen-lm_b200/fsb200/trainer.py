@@ -91,6 +91,8 @@ class PretrainStep:
             out.loss.backward()
             eng.backward_done()
             self._loss_acc += out.loss.detach()
+        if eng.hyper is not None:      # device-side scalars are in use (graph mode switched off for a while): keep them current
+            eng.set_device_hyper(self.lr_fn(self.global_step))
         eng.step(lr=self.lr_fn(self.global_step))
         self.global_step += 1
         return self._loss_acc / len(device_batches)
