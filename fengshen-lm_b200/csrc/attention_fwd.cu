@@ -281,6 +281,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld32_at<0>(a, dst);
       tmem_ld32_at<32>(a + 32, dst);
     };
+    // Same, but only if S(j) has already landed (warp-uniform answer: tcgen05.ld is warp-collective). In steady state the
+    // tensor core is still busy with the other Q tile's products when this is asked, so the blocking form runs after the
+    // exponentials instead of in front of them (a cycle trace showed 250-420 cycles per step spent waiting here).
+    auto try_load_s = [&](int j, uint32_t (&dst)[64]) -> bool {
+      if (!__all_sync(0xffffffffu, mbar_test(&s_full[slot * 2 + (j & 1)], (j >> 1) & 1))) return false;
+      tc_fence_after();
+      const uint32_t a = t_slot + (j & 1) * ATT_BKV;
+      tmem_ld32_at<0>(a, dst);
+      tmem_ld32_at<32>(a + 32, dst);
+      return true;
+    };
     auto step = [&](int j, uint32_t (&cur)[64], uint32_t (&nxt)[64]) {
       const int buf = j & 1;
       FTRACE(0, j, 0);
@@ -341,8 +352,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (raise) m_ref = mx;
       const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;
       FTRACE(0, j, 3);
-      // prefetch S(j+1) into the other register set while this step's exponentials run
-      if (j + 1 < n_mine) load_s(j + 1, nxt);
+      // prefetch S(j+1) into the other register set while this step's exponentials run — if it is there already
+      const bool more = j + 1 < n_mine;
+      const bool prefetched = more && try_load_s(j + 1, nxt);
       FTRACE(0, j, 4);
       if constexpr (kPT) {
 #pragma unroll
@@ -378,6 +390,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       tc_fence_before();     // order our tcgen05.ld/st before the MMAs that read / overwrite TMEM
       mbar_arrive(&p_ready[slot * 2 + buf]);
+      if (more && !prefetched) load_s(j + 1, nxt);   // its latency hides behind the next step's first instructions
       FTRACE(0, j, 6);
     };
     if (n_mine > 0) load_s(0, sa);
