@@ -40,6 +40,7 @@ struct GemmParams {
   int tma_store;   // bf16 D without accumulate: stage through smem and write with cp.async.bulk.tensor (full lines)
   int tiles_m, tiles_n;
   int group_m;     // m-tiles per rasterisation group (see fsb_gemm_bf16)
+  int l2_hints;    // bit 0: A panels evict-last, bit 1: B panels evict-first, bit 2: D stores evict-first (FSB_GEMM_L2HINT)
 };
 
 // kAux: the GEMM also writes the pre-activation (GELU MLPs): two bulk stores per column group. Their smem->global reads
@@ -159,9 +160,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       // (pair) both CTAs load their own halves; every transaction is credited to the LEADER's full barrier, on which the
       // leader alone posts the expected byte count of the whole pair
-      auto load = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
-        if constexpr (kCta2) tma_load_3d_2cta(dst, tm, mapa_shared(smem_u32(bar), 0), c0, c1, c2);
-        else tma_load_3d(dst, tm, bar, c0, c1, c2);
+      // L2 policy: tiles are walked m-fastest inside a group of m-tiles, so a group's A panels are read again for every
+      // n-tile of the sweep (keep them: evict-last) while a B panel is used by the CTAs of one wave and then dead (evict-
+      // first); ncu showed the 8192x15360x5120 GEMM reading 738 MB for 241 MB of operands without the hints.
+      const uint64_t pol_a = (p.l2_hints & 1) ? kL2EvictLast : kL2EvictNormal, pol_b = (p.l2_hints & 2) ? kL2EvictFirst : kL2EvictNormal;
+      const bool hints = (p.l2_hints & 3) != 0;
+      auto load = [&](uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, uint64_t policy) {
+        if (hints) {
+          if constexpr (kCta2) tma_load_3d_2cta_hint(dst, tm, mapa_shared(smem_u32(bar), 0), c0, c1, c2, policy);
+          else tma_load_3d_hint(dst, tm, bar, c0, c1, c2, policy);
+        } else {
+          if constexpr (kCta2) tma_load_3d_2cta(dst, tm, mapa_shared(smem_u32(bar), 0), c0, c1, c2);
+          else tma_load_3d(dst, tm, bar, c0, c1, c2);
+        }
       };
       for (int t = tile_first; t < num_tiles; t += tile_step) {
         int b, m_idx, n_idx;
@@ -174,18 +185,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (!kCta2 || cta_rank == 0) mbar_expect_tx(&full_bar[stage], S::STAGE_BYTES * (kCta2 ? 2 : 1));
           const int k0 = kb * GEMM_BK;
           if constexpr (!A_MN) {
-            load(sa, &tmA, &full_bar[stage], k0, m0, b);
+            load(sa, &tmA, &full_bar[stage], k0, m0, b, pol_a);
           } else {
 #pragma unroll
             for (int c = 0; c < GEMM_BM / 64; ++c)
-              load(sa + c * (GEMM_BK * 128), &tmA, &full_bar[stage], m0 + c * 64, k0, b);
+              load(sa + c * (GEMM_BK * 128), &tmA, &full_bar[stage], m0 + c * 64, k0, b, pol_a);
           }
           if constexpr (!B_MN) {
-            load(sb, &tmB, &full_bar[stage], k0, n0, b);
+            load(sb, &tmB, &full_bar[stage], k0, n0, b, pol_b);
           } else {
 #pragma unroll
             for (int c = 0; c < BNL / 64; ++c)
-              load(sb + c * (GEMM_BK * 128), &tmB, &full_bar[stage], n0 + c * 64, k0, b);
+              load(sb + c * (GEMM_BK * 128), &tmB, &full_bar[stage], n0 + c * 64, k0, b, pol_b);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -268,7 +279,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_3d(tm, stg, c0, r0, bz);
+          if (p.l2_hints & 4) tma_store_3d_hint(tm, stg, c0, r0, bz, kL2EvictFirst);
+          else tma_store_3d(tm, stg, c0, r0, bz);
           tma_store_commit();
         }
         ++item;
@@ -680,6 +692,8 @@ static int fsb::gemm_impl(int layout, int64_t M, int64_t N, int64_t K, const voi
   p.M = int(M); p.N = int(N); p.K = int(K); p.batch = int(batch);
   p.d_f32 = (d_dtype == FSB_F32); p.bias_f32 = (bias_dtype == FSB_F32);
   p.epilogue = epilogue; p.accumulate = accumulate;
+  static const int l2hint_env = [] { const char* e = getenv("FSB_GEMM_L2HINT"); return e ? atoi(e) : 0; }();
+  p.l2_hints = l2hint_env;
   p.tiles_m = cta2 ? int((M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) : int((M + GEMM_BM - 1) / GEMM_BM);
   p.tiles_n = int((N + BN - 1) / BN);
   // Rasterisation: tiles are walked m-fastest inside groups of group_m m-tiles, so one wave of CTAs touches group_m A panels
