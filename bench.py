@@ -633,6 +633,9 @@ def main():
             "roofline": main_run["roofline"], "e2e": main_run["e2e"], "gpu_launches": main_run["launches"],
             "clocks": main_run["clocks"], "final_loss": main_run["final_loss"], "memory_bytes": main_run["memory"],
             "comm_bytes_per_step_per_gpu": main_run["comm_bytes_per_step_per_gpu"]}
+    if os.environ.get("FSB_ENGINE_SKIP_COLLECTIVES", "0") == "1":
+        line["INVALID_diagnostic"] = ("FSB_ENGINE_SKIP_COLLECTIVES=1: the NCCL calls were dropped (results are wrong); this line only "
+                                      "measures the step WITHOUT communication — subtract from the normal run to get the exposed comm")
     if graph_block is not None:
         line["cuda_graph_step"] = graph_block
     if parity is not None:

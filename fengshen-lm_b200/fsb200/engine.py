@@ -87,6 +87,10 @@ class ZeroEngine:
         # points (comm_backend="fsb": the C-ABI a non-PyTorch host binds; torch.distributed then only carries the
         # 128-byte NCCL id at start-up).
         self.fsb_comm = None
+        # DIAGNOSTIC ONLY (results are wrong): FSB_ENGINE_SKIP_COLLECTIVES=1 keeps every stream / event / kernel of the step but
+        # drops the NCCL calls — step time with minus step time without is the EXPOSED communication (bench.py `comm_probe`)
+        import os
+        self.skip_collectives = os.environ.get("FSB_ENGINE_SKIP_COLLECTIVES", "0") == "1"
         if comm_backend not in ("torch", "fsb"):
             raise ValueError(f"comm_backend {comm_backend!r}: expected 'torch' or 'fsb'")
         if comm_backend == "fsb" and self.world > 1:
@@ -180,12 +184,16 @@ class ZeroEngine:
             self.k.accumulate(self._seg(self.acc32, i), self.flat.bucket_view(i, grad=True), 1.0, overwrite=first)
 
     def _reduce_scatter(self, out, full):
+        if self.skip_collectives:
+            return
         if self.fsb_comm is not None:
             self.fsb_comm.reduce_scatter(out, full)
         else:
             dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM, group=self.pg)
 
     def _all_gather(self, full, mine):
+        if self.skip_collectives:
+            return
         if self.fsb_comm is not None:
             self.fsb_comm.all_gather(full, mine)
         else:
@@ -250,7 +258,7 @@ class ZeroEngine:
                 if not first_rep:
                     self.sumsq.add_(self.sumsq_rep, alpha=1.0 / self.tp)
                 dist.all_reduce(self.sumsq, op=dist.ReduceOp.SUM, group=self.tp_group)
-            if self.world > 1:
+            if self.world > 1 and not self.skip_collectives:
                 if self.fsb_comm is not None:
                     self.fsb_comm.all_reduce(self.sumsq)
                 else:
