@@ -25,11 +25,14 @@
 namespace fsb {
 
 constexpr int ATT_BQ = 128;   // rows per Q tile (= TMEM lanes)
-constexpr int ATT_NQ = 2;     // Q tiles per CTA
+// Q tiles per CTA (template parameter NQ): 2 = one CTA per SM working on two tiles; 1 = one tile per CTA and TWO CTAs per SM
+// (256 TMEM columns, ~97 KB of shared memory, 256 threads each): the same two tiles per SM, but as independent CTAs — one CTA's
+// prologue (TMEM allocation, barrier set-up, Q / first K, V round trips) and epilogue overlap the other's key loop, and the
+// two softmax groups are no longer marched in lockstep by a shared MMA-issue warp. At S <= 1024 the per-CTA fixed cost is of
+// the order of the key loop itself (D = 64: 250 TFLOP/s at S = 1024 against 400 at S = 8192 with NQ = 2).
 constexpr int ATT_BKV = 64;   // keys per inner step
 constexpr int ATT_GROUP = 128;                       // softmax threads per Q tile (one per row)
-constexpr int ATT_THREADS = ATT_NQ * ATT_GROUP + 128; // + warpgroup 2: TMA warp, MMA warp, two idle warps (setmaxnreg donors)
-constexpr int ATT_W_TMA = 8, ATT_W_MMA = 9;
+// threads = NQ * 128 softmax + one more warpgroup: TMA warp, MMA warp, two idle warps (setmaxnreg donors)
 constexpr float ATT_RESCALE_TAU = 8.0f;              // log2 units
 // setmaxnreg split (a warpgroup shares one value): 256 softmax threads x ATT_SM_REGS + 128 (TMA / MMA / idle) x ATT_WG2_REGS
 // <= 65536. The softmax threads hold two 64-score register sets (S(j) and the prefetched S(j+1)): every register they do not
@@ -43,22 +46,26 @@ constexpr float ATT_RESCALE_TAU = 8.0f;              // log2 units
 // 216 / 72 leaves 1024 registers of the SM unclaimed. Do NOT close that gap: 232 / 48 (exactly 65536) never gets its
 // setmaxnreg.inc granted and the kernel hangs (measured the hard way, round 2).
 static_assert(256 * ATT_SM_REGS + 128 * ATT_WG2_REGS <= 65536 - 1024, "register file (keep the launch-time slack)");
+// NQ = 1 (two CTAs per SM, 128 + 128 threads each): 2 * 128 * (192 + 48) = 61440
+constexpr int ATT1_SM_REGS = 192, ATT1_WG2_REGS = 48;
 
-template <int D>
+template <int D, int NQ>
 struct AttFwdSmem {
-  static constexpr int STAGES = (D == 128) ? 3 : 6;        // K/V ring depth (must cover the TMA round trip)
+  // K/V ring depth (must cover the TMA round trip); NQ = 1 has to fit twice into an SM's shared memory
+  static constexpr int STAGES = NQ == 2 ? ((D == 128) ? 3 : 6) : ((D == 128) ? 2 : 5);
   static constexpr int Q_BYTES = ATT_BQ * D * 2;           // per slot
   static constexpr int KV_BYTES = ATT_BKV * D * 2;         // per tensor per stage
   static constexpr int P_BYTES = ATT_BQ * ATT_BKV * 2;     // per slot per buffer
   static constexpr int OFF_Q = 0;
-  static constexpr int OFF_K = OFF_Q + ATT_NQ * Q_BYTES;
+  static constexpr int OFF_K = OFF_Q + NQ * Q_BYTES;
   static constexpr int OFF_V = OFF_K + STAGES * KV_BYTES;
   static constexpr int OFF_P = OFF_V + STAGES * KV_BYTES;  // [slot][buf]
-  static constexpr int OFF_BAR = OFF_P + ATT_NQ * 2 * P_BYTES;
+  static constexpr int OFF_BAR = OFF_P + (NQ == 2 ? NQ * 2 * P_BYTES : 0);   // NQ = 1: P only ever travels through TMEM
   // q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2][2], p_ready[2][2], o_done[2]
   static constexpr int NBAR = 1 + 4 * STAGES + 10;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into on sm_100");
+  static_assert(NQ == 2 || TOTAL + 1024 <= 232448 / 2, "NQ = 1 is meant to run two CTAs per SM");
 };
 
 struct AttFwdParams {
@@ -85,17 +92,20 @@ __device__ long long g_fwd_trace[2][64][8];
 // pairs, 32 columns) over the first half of the S(j) columns it has just consumed and the tensor core reads the A operand
 // from there (tcgen05.mma with a TMEM A operand, as the backward kernels do for dS): per 64-key step and Q tile that removes a
 // 16 KB shared-memory write, a 16 KB operand read and the generic->async proxy fence from the shared-memory-bound loop.
-template <int D, bool kBias, bool kPT>
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <int D, bool kBias, bool kPT, int NQ>
+__global__ void __launch_bounds__(NQ * ATT_GROUP + 128, NQ == 1 ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttFwdParams p) {
-  using S = AttFwdSmem<D>;
+  using S = AttFwdSmem<D, NQ>;
+  constexpr int ATT_NQ = NQ;
+  constexpr int ATT_W_TMA = NQ * 4, ATT_W_MMA = NQ * 4 + 1;
+  static_assert(NQ == 2 || kPT, "one Q tile per CTA relies on the TMEM hand-over of P (no P tile in shared memory)");
   constexpr int STAGES = S::STAGES;
-  constexpr int TMEM_COLS = 512;
+  constexpr int TMEM_COLS = NQ == 2 ? 512 : 256;
   constexpr int SLOT_COLS = 2 * ATT_BKV + D;  // S[2] | O   per Q tile
   constexpr uint32_t IDESC_S = make_idesc_bf16(ATT_BQ, ATT_BKV, 0, 0);
   constexpr uint32_t IDESC_PV = make_idesc_bf16(ATT_BQ, D, 0, 1);
-  static_assert(ATT_NQ * SLOT_COLS <= 512, "TMEM budget");
+  static_assert(ATT_NQ * SLOT_COLS <= TMEM_COLS, "TMEM budget");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -124,7 +134,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     else if (p.causal) n_kv[i] = min(n_all, (min(qs + ATT_BQ, p.seq_q) + ATT_BKV - 1) / ATT_BKV);
     else n_kv[i] = n_all;
   }
-  const int n_total = max(n_kv[0], n_kv[1]);
+  const int n_total = NQ == 2 ? max(n_kv[0], n_kv[NQ - 1]) : n_kv[0];
 #ifdef FSB_ATTN_TRACE
   const bool ftrace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 &&
                          (warp == 4 || warp == ATT_W_MMA);   // slot-1 math warp (most steps) and the MMA warp
@@ -150,13 +160,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   // register split: see ATT_SM_REGS / ATT_WG2_REGS
   if (warp > ATT_W_MMA) {
-    reg_dec<ATT_WG2_REGS>();   // idle donor warps
+    reg_dec<(NQ == 2 ? ATT_WG2_REGS : ATT1_WG2_REGS)>();   // idle donor warps
   } else if (warp == ATT_W_TMA) {
     // ===================== TMA producer =====================
-    reg_dec<ATT_WG2_REGS>();
+    reg_dec<(NQ == 2 ? ATT_WG2_REGS : ATT1_WG2_REGS)>();
     if (lane == 0) {
       const int qc = head * p.q_head_stride, kc = head * p.k_head_stride, vc = head * p.v_head_stride;
-      const int active = (n_kv[0] > 0) + (n_kv[1] > 0);
+      const int active = (n_kv[0] > 0) + (NQ == 2 ? int(n_kv[NQ - 1] > 0) : 0);
       mbar_expect_tx(q_full, active * S::Q_BYTES);
 #pragma unroll
       for (int i = 0; i < ATT_NQ; ++i) {
@@ -184,7 +194,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else if (warp == ATT_W_MMA) {
     // ===================== MMA issuer: warp-uniform loop, one elected lane issues =====================
-    reg_dec<ATT_WG2_REGS>();
+    reg_dec<(NQ == 2 ? ATT_WG2_REGS : ATT1_WG2_REGS)>();
     const uint64_t dsc_q = make_smem_desc_sw128(smem_u32(smem + S::OFF_Q), 0, 1024);
     const uint64_t dsc_k = make_smem_desc_sw128(smem_u32(smem + S::OFF_K), 0, 1024);
     const uint64_t dsc_p = make_smem_desc_sw128(smem_u32(smem + S::OFF_P), 0, 1024);
@@ -254,7 +264,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
   } else {
     // ===================== softmax groups: one thread per query row =====================
-    reg_inc<ATT_SM_REGS>();
+    reg_inc<(NQ == 2 ? ATT_SM_REGS : ATT1_SM_REGS)>();
     const int slot = warp >> 2;
     const int quad = warp & 3;                    // TMEM lane quadrant this warp may access (= warp id % 4)
     const int r_in = quad * 32 + lane;            // row inside the tile == TMEM lane
@@ -264,6 +274,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int sw = r_in & 7;
     const uint8_t* mrow = p.kv_mask ? p.kv_mask + int64_t(b) * p.seq_kv : nullptr;
     const float sc = p.scale_log2;
+    const int kmax = p.causal ? min(q_row, p.seq_kv - 1) : p.seq_kv - 1;   // last key column this row may attend to
     // T5 / mT5 relative-position bias (transformers mt5/modeling_mt5.py:181-235,:320): bias[h, q, k] depends on k - q only, so it
     // arrives as one vector per head; this row reads the 64 consecutive entries starting at (c0 - q_row + seq_q - 1).
     const int n_rel = p.seq_q + p.seq_kv - 1;
@@ -312,12 +323,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       const bool need_mask = (p.causal && c0 + ATT_BKV - 1 > q0 + slot * ATT_BQ) || (c0 + ATT_BKV > p.seq_kv) || mrow;
       if (need_mask) {
+        if (mrow == nullptr) {
+          // causal / ragged-tail masking is a per-row column LIMIT: one compare + select per score. (At S <= 1024 a third or
+          // more of all steps touch the diagonal, so this path is as hot as the unmasked one.)
+          const int lim = kmax - c0;              // keep columns c <= lim
 #pragma unroll
-        for (int c = 0; c < 64; ++c) {
-          const int col = c0 + c;
-          bool keep = col < p.seq_kv && !(p.causal && col > q_row);
-          if (keep && mrow) keep = mrow[col] != 0;
-          if (!keep) cur[c] = 0xff800000u;        // -inf
+          for (int c = 0; c < 64; ++c) cur[c] = (c <= lim) ? cur[c] : 0xff800000u;   // -inf
+        } else {
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const int col = c0 + c;
+            bool keep = col < p.seq_kv && !(p.causal && col > q_row);
+            if (keep) keep = mrow[col] != 0;
+            if (!keep) cur[c] = 0xff800000u;      // -inf
+          }
         }
       }
       float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -443,22 +462,25 @@ int make_attn_tmap(CUtensorMap* tm, const void* base, int64_t row_stride, int64_
   return make_tmap_bf16(tm, base, 3, dims, strides, box);
 }
 
-template <int D, bool kBias, bool kPT>
+template <int D, bool kBias, bool kPT, int NQ>
 static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttFwdParams& p,
                            cudaStream_t st) {
-  using S = AttFwdSmem<D>;
+  using S = AttFwdSmem<D, NQ>;
+  constexpr int ATT_NQ = NQ;
   static bool configured = false;
-  auto kern = attn_fwd_kernel<D, kBias, kPT>;
+  auto kern = attn_fwd_kernel<D, kBias, kPT, NQ>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
     if (e != cudaSuccess) {
       set_error("sdpa_fwd: cudaFuncSetAttribute(%d) failed: %s", S::TOTAL, cudaGetErrorString(e));
       return FSB_ERR_CUDA;
     }
+    if (NQ == 1)   // two CTAs per SM only fit with the largest shared-memory carve-out
+      cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   dim3 grid((p.seq_q + ATT_NQ * ATT_BQ - 1) / (ATT_NQ * ATT_BQ), p.nheads, p.batch);
-  kern<<<grid, ATT_THREADS, S::TOTAL, st>>>(tq, tk, tv, p);
+  kern<<<grid, NQ * ATT_GROUP + 128, S::TOTAL, st>>>(tq, tk, tv, p);
   FSB_CUDA_LAUNCH_CHECK();
   return FSB_OK;
 }
@@ -501,8 +523,12 @@ extern "C" int fsb_sdpa_fwd(const void* q, const void* k, const void* v, void* o
   p.scale_log2 = scale * 1.4426950408889634f;
   // FSB_ATTN_P_TMEM=0 selects the shared-memory P hand-over (A/B measurements); default: through tensor memory
   static const bool p_tmem = [] { const char* e = getenv("FSB_ATTN_P_TMEM"); return e ? atoi(e) != 0 : true; }();
-#define FSB_FWD(DD, BB) (p_tmem ? launch_attn_fwd<DD, BB, true>(tq, tk, tv, p, (cudaStream_t)st) \
-                                : launch_attn_fwd<DD, BB, false>(tq, tk, tv, p, (cudaStream_t)st))
+  // FSB_ATTN_NQ=1|2 forces one / two Q tiles per CTA (default below; see the NQ note at the top of the file)
+  static const int nq_env = [] { const char* e = getenv("FSB_ATTN_NQ"); return e ? atoi(e) : 0; }();
+  const int nq = (nq_env == 1 || nq_env == 2) ? nq_env : 2;
+#define FSB_FWD(DD, BB) (!p_tmem ? launch_attn_fwd<DD, BB, false, 2>(tq, tk, tv, p, (cudaStream_t)st)                 \
+                         : nq == 1 ? launch_attn_fwd<DD, BB, true, 1>(tq, tk, tv, p, (cudaStream_t)st)               \
+                                   : launch_attn_fwd<DD, BB, true, 2>(tq, tk, tv, p, (cudaStream_t)st))
   if (rel_bias != nullptr) return head_dim == 128 ? FSB_FWD(128, true) : FSB_FWD(64, true);
   return head_dim == 128 ? FSB_FWD(128, false) : FSB_FWD(64, false);
 #undef FSB_FWD
