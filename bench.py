@@ -466,7 +466,7 @@ def parity_block(world, rank, device):
     from types import SimpleNamespace
     from fsb200.engine import ZeroEngine
     from fsb200.models.llama import LlamaForCausalLM
-    V, h, nl, nh, S, steps, per_rank = 512, 256, 2, 4, 64, 3, 2
+    V, h, nl, nh, S, steps, per_rank = 512, 256, 3, 4, 64, 3, 2   # 3 layers: the ZeRO-2 gradient slots rotate
     cfg = SimpleNamespace(vocab_size=V, hidden_size=h, num_hidden_layers=nl, num_attention_heads=nh, rms_norm_epsilon=1e-6,
                           max_position_embeddings=2048, rotary_emb_base=10000, llama_mlp_multiple_of=256)
     solo_groups = [dist.new_group(ranks=[r]) for r in range(world)]   # collective: every rank creates every group
