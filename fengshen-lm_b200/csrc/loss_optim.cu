@@ -68,16 +68,29 @@ __global__ void __launch_bounds__(XENT_THREADS) xent_fwd_bwd_kernel(
     float lab_logit = 0.f;  // read before pass 2 may overwrite it (dlogits may alias logits)
     if (threadIdx.x == 0) lab_logit = __bfloat162float(logits[t * ld + lab]);
     float m = -INFINITY, sum = 0.f;
-    for (int i = threadIdx.x; i < nv; i += XENT_THREADS) {
-      const uint4 q = row[i];
-      float f[8] = {bf16lo(q.x), bf16hi(q.x), bf16lo(q.y), bf16hi(q.y), bf16lo(q.z), bf16hi(q.z), bf16lo(q.w), bf16hi(q.w)};
-      float lm = f[0];
+    // four independent 16-byte loads in flight per thread and iteration (the single-load form left the row fetch latency-
+    // bound: 4.1 TB/s of DRAM-level traffic on [32768, 50264]); one running-max update per 32 values
+    for (int i0 = threadIdx.x; i0 < nv; i0 += 4 * XENT_THREADS) {
+      uint4 q[4];
 #pragma unroll
-      for (int j = 1; j < 8; ++j) lm = fmaxf(lm, f[j]);
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * XENT_THREADS;
+        q[u] = i < nv ? row[i] : make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // bf16 -inf pairs
+      }
+      float f[4][8];
+      float lm = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        unpack8(q[u], f[u]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) lm = fmaxf(lm, f[u][j]);
+      }
       const float nm = fmaxf(m, lm);
       float acc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc += __expf(f[j] - nm);
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += __expf(f[u][j] - nm);    // exp(-inf) = 0 for the padding lanes
       sum = sum * __expf(m - nm) + acc;
       m = nm;
     }
@@ -102,20 +115,28 @@ __global__ void __launch_bounds__(XENT_THREADS) xent_fwd_bwd_kernel(
     if (drow) {
       const float scale = grad_scale / float(*n_valid);
       const float inv = 1.f / gsum;
-      for (int i = threadIdx.x; i < nv; i += XENT_THREADS) {
-        const uint4 q = row[i];
-        float f[8] = {bf16lo(q.x), bf16hi(q.x), bf16lo(q.y), bf16hi(q.y), bf16lo(q.z), bf16hi(q.z), bf16lo(q.w), bf16hi(q.w)};
-        const int c0 = i * 8;
+      for (int i0 = threadIdx.x; i0 < nv; i0 += 4 * XENT_THREADS) {
+        uint4 q[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float p = __expf(f[j] - gmax) * inv;
-          if (c0 + j == lab) p -= 1.f;
-          f[j] = p * scale;
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * XENT_THREADS;
+          if (i < nv) q[u] = row[i];
         }
-        uint4 o;
-        o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-        o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-        drow[i] = o;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * XENT_THREADS;
+          if (i >= nv) continue;
+          float f[8];
+          unpack8(q[u], f);
+          const int c0 = i * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float p = __expf(f[j] - gmax) * inv;
+            if (c0 + j == lab) p -= 1.f;
+            f[j] = p * scale;
+          }
+          drow[i] = pack8(f);
+        }
       }
     }
   }
