@@ -537,6 +537,9 @@ def main():
                     help="SMs the persistent GEMM grids leave to overlapping NCCL kernels (multi-GPU only)")
     ap.add_argument("--cuda-graph", type=int, default=0,
                     help="1: capture the whole optimizer step in a CUDA graph and replay it (single GPU; launch-bound configs)")
+    ap.add_argument("--headline-zero-stage", type=int, default=0,
+                    help="override the ZeRO stage of the headline block (diagnostic: 1 = reduce once per optimizer step instead of "
+                         "once per micro-batch; BASELINE's C4 is stage 2)")
     ap.add_argument("--no-graph-block", action="store_true", help="skip the extra CUDA-graph measurement at --gpus 1")
     ap.add_argument("--breakdown", action="store_true",
                     help="after the timed runs, profile 2 more steps with CUDA events around every fsb_* call and print the "
@@ -608,7 +611,9 @@ def main():
     headline = None
     if args.gpus in HEADLINE and not args.no_headline and args.workload == "gpt2-110m":
         hname, hsteps, hwarm = HEADLINE[args.gpus]
-        hr = run_workload(hname, args, world, rank, device, pg, hsteps, hwarm, want_e2e=not args.no_e2e, profile_steps=1)
+        hover = {"stage": args.headline_zero_stage} if args.headline_zero_stage else None
+        hr = run_workload(hname, args, world, rank, device, pg, hsteps, hwarm, want_e2e=not args.no_e2e, profile_steps=1,
+                          overrides=hover)
         headline = {"workload": hr["workload"], "name": hname, "n_gpus": args.gpus, "tokens_per_s": hr["value"],
                     "ms_per_step": hr["ms_per_step"], "steps": hsteps, "warmup": hwarm, "e2e": hr["e2e"],
                     "global_batch": hr["w"]["per_gpu"] * args.gpus, "micro_batch": hr["w"]["micro"], "grad_accum": hr["ga"],
