@@ -632,11 +632,16 @@ def main():
             # the same model and batch with ZeRO STAGE 1 semantics (full bf16 gradients accumulate locally, ONE reduce-scatter
             # per bucket and optimizer step instead of one per micro-batch): 1/8 of the gradient traffic and no per-micro-batch
             # fp32 shard accumulation. 131 GB peak per GPU — on 180 GB parts gradient sharding is not needed for this model.
-            vr = run_workload(hname, args, world, rank, device, pg, 3, 1, want_e2e=False, profile_steps=0, overrides={"stage": 1})
-            headline["zero1_variant"] = {"tokens_per_s": vr["value"], "ms_per_step": vr["ms_per_step"], "steps": 3, "warmup": 1,
-                                         "step_frac_of_sustained_peak": vr["roofline"]["step_frac"],
-                                         "final_loss": vr["final_loss"], "memory_bytes": vr["memory"],
-                                         "comm_bytes_per_step_per_gpu": vr["comm_bytes_per_step_per_gpu"]}
+            try:   # memory is symmetric across ranks: an out-of-memory here hits every rank at model construction, before any collective
+                vr = run_workload(hname, args, world, rank, device, pg, 3, 1, want_e2e=False, profile_steps=0,
+                                  overrides={"stage": 1})
+                headline["zero1_variant"] = {"tokens_per_s": vr["value"], "ms_per_step": vr["ms_per_step"], "steps": 3, "warmup": 1,
+                                             "step_frac_of_sustained_peak": vr["roofline"]["step_frac"],
+                                             "final_loss": vr["final_loss"], "memory_bytes": vr["memory"],
+                                             "comm_bytes_per_step_per_gpu": vr["comm_bytes_per_step_per_gpu"]}
+            except torch.cuda.OutOfMemoryError as e:
+                headline["zero1_variant"] = {"error": f"out of memory: {str(e)[:120]}"}
+                torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
