@@ -637,7 +637,7 @@ def main():
                                   overrides={"stage": 1})
                 headline["zero1_variant"] = {"tokens_per_s": vr["value"], "ms_per_step": vr["ms_per_step"], "steps": 3, "warmup": 1,
                                              "step_frac_of_sustained_peak": vr["roofline"]["step_frac"],
-                                             "final_loss": vr["final_loss"], "memory_bytes": vr["memory"],
+                                             "final_loss": vr["final_loss"], "clocks": vr["clocks"], "memory_bytes": vr["memory"],
                                              "comm_bytes_per_step_per_gpu": vr["comm_bytes_per_step_per_gpu"]}
             except torch.cuda.OutOfMemoryError as e:
                 headline["zero1_variant"] = {"error": f"out of memory: {str(e)[:120]}"}
