@@ -250,7 +250,8 @@ class Trainer:
         module = self.lightning_module
         if self.engine is not None:
             self.engine.wait_params()   # the parameter all-gather of the last step may still be in flight
-        consumed = self.global_step * self.accumulate_grad_batches * self.world_size * \
+        tp = getattr(self._find_fsb_model(module), "tp", 1) if module is not None else 1
+        consumed = self.global_step * self.accumulate_grad_batches * (self.world_size // max(1, tp)) * \
             int(getattr(getattr(self.datamodule, "hparams", {}), "train_batchsize", 1) or 1)
         if self.global_rank == 0:
             state = {"module": {k: v.detach().cpu() for k, v in module.state_dict().items()},
