@@ -235,6 +235,11 @@ class GPT2LMHeadModel(nn.Module):
         self._done("wte")
         self._done("no_decay")
 
+    def save_pretrained(self, path, **_):
+        """HF-style export (config.json + pytorch_model.bin with this class's HF key names): fsb200/models/export.py."""
+        from .export import save_pretrained
+        save_pretrained(self, path)
+
     def _done(self, bucket):
         if self.grad_hook is not None:
             self.grad_hook(bucket)

@@ -193,6 +193,11 @@ class MT5ForConditionalGeneration(nn.Module):
                 raise ValueError(f"shape mismatch for {k}: {tuple(sd[k].shape)} vs {tuple(prm.shape)}")
             prm.copy_(sd[k].to(device=prm.device, dtype=prm.dtype))
 
+    def save_pretrained(self, path, **_):
+        """HF-style export (config.json + pytorch_model.bin with this class's HF key names): fsb200/models/export.py."""
+        from .export import save_pretrained
+        save_pretrained(self, path)
+
     # ---- engine hooks -----------------------------------------------------------------------------------------------
     def _done(self, bucket):
         if self.grad_hook is not None and bucket in self.flat.bucket_index:   # "head" does not exist with a tied LM head

@@ -156,3 +156,22 @@ def test_mt5_grad_accumulation_rotating_slots_match_full_batch():
     e2.step()
     d = (one.flat.params.float() - two.flat.params.float()).abs().max().item()
     assert d <= 2e-2, d   # bf16 parameters after one lr=1e-3 step: one ulp at |w| ~ 2 is 1.6e-2
+
+
+def test_mt5_save_pretrained_is_readable_by_transformers(tmp_path):
+    """pretrain_t5.py:105-112 ends a run with `self.model.save_pretrained(...)`: the exported directory must load into the HF class
+    the reference uses, and give the same loss there (CPU, fp32 arithmetic on the exported bf16 weights)."""
+    from transformers import MT5ForConditionalGeneration as HFMT5
+    from fsb200.models.export import from_pretrained
+    ref = H.build_mt5(H.MT5_SMALL, seed=5)
+    mine = _mine(ref)
+    batch = H.make_t5_batch(H.MT5_SMALL["vocab_size"], 2, 64, 32, seed=77)
+    mine.save_pretrained(str(tmp_path / "exp"))
+    hf = HFMT5.from_pretrained(str(tmp_path / "exp"), torch_dtype=torch.float32, attn_implementation="eager")
+    hf.eval()
+    with torch.no_grad():
+        want = ref(**batch).loss.item()
+        got_hf = hf(**batch).loss.item()
+    assert abs(got_hf - want) <= 1e-4 * max(1.0, abs(want)), (got_hf, want)
+    back = from_pretrained(MT5ForConditionalGeneration, str(tmp_path / "exp"), config_cls=type(ref.config), device="cuda")
+    assert torch.equal(back.flat.params, mine.flat.params)
