@@ -159,6 +159,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     fence_barrier_init();
   }
   if (warp == AB_W_MMA) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  // relative-position bias: the window of this head's vector the CTA can touch, in shared memory (the dS tile buffers of the
+  // pre-TMEM design are unused), pre-multiplied by log2 e and zero-padded past the vector
+  [[maybe_unused]] const int b_lo = (p.seq_q - 1) - min(q0 + AB_BM - 1, p.seq_q - 1);
+  [[maybe_unused]] const int b_len = AB_BM + n_steps * AB_BN;
+  [[maybe_unused]] const bool bias_in_smem = kBias && b_len <= (2 * S::T_BYTES) / 4;
+  if constexpr (kBias) {
+    if (bias_in_smem) {
+      float* bs = reinterpret_cast<float*>(smem + S::OFF_T0);
+      const int n_rel_ = p.seq_q + p.seq_kv - 1;
+      const float* src = p.rel_bias + int64_t(head) * n_rel_ + b_lo;
+      for (int i = threadIdx.x; i < b_len; i += AB_THREADS) bs[i] = (b_lo + i < n_rel_) ? __ldg(src + i) * 1.4426950408889634f : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -267,6 +280,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // relative-position bias (mT5): this row reads entries (c0 + c - q_row + seq_q - 1) of its head's vector
     const int n_rel = p.seq_q + p.seq_kv - 1;
     const float* brow = kBias ? p.rel_bias + int64_t(head) * n_rel + (p.seq_q - 1 - min(q_row, p.seq_q - 1)) : nullptr;
+    [[maybe_unused]] const int bias_k0 = (p.seq_q - 1 - min(q_row, p.seq_q - 1)) - b_lo;   // this row's offset into the smem window
     float* dpart = kBias && p.dbias_part
                        ? p.dbias_part + (((int64_t(b) * p.nheads + head) * gridDim.x + tile) * (AB_MATH / 32) + warp) * p.dbias_tstride
                        : nullptr;
@@ -308,8 +322,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       [[maybe_unused]] float ds[AB_PC];   // dS in fp32 (for the bias gradient)
       if constexpr (kBias) {
         constexpr float kLog2e = 1.4426950408889634f;
+        if (bias_in_smem) {
+          const float* bs = reinterpret_cast<const float*>(smem + S::OFF_T0) + bias_k0 + c0;
 #pragma unroll
-        for (int c = 0; c < AB_PC; ++c) bl[c] = __ldg(brow + min(c0 + c, p.seq_kv - 1)) * kLog2e;
+          for (int c = 0; c < AB_PC; ++c) bl[c] = bs[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < AB_PC; ++c) bl[c] = __ldg(brow + min(c0 + c, p.seq_kv - 1)) * kLog2e;
+        }
       }
       if (!need_mask) {
 #pragma unroll

@@ -61,6 +61,9 @@ struct AttFwdSmem {
   static constexpr int OFF_V = OFF_K + STAGES * KV_BYTES;
   static constexpr int OFF_P = OFF_V + STAGES * KV_BYTES;  // [slot][buf]
   static constexpr int OFF_BAR = OFF_P + (NQ == 2 ? NQ * 2 * P_BYTES : 0);   // NQ = 1: P only ever travels through TMEM
+  // relative-position bias window (kBias && kPT && NQ == 2): the P tiles are not used with the TMEM hand-over, so their 64 KB hold
+  // the fp32 window of the head's bias vector this CTA can touch (pre-multiplied by log2 e): NQ * 128 + seq_kv (+63) entries
+  static constexpr int BIAS_FLOATS = (NQ == 2) ? (NQ * 2 * P_BYTES) / 4 : 0;
   // q_full, k_full[S], k_empty[S], v_full[S], v_empty[S], s_full[2][2], p_ready[2][2], o_done[2]
   static constexpr int NBAR = 1 + 4 * STAGES + 10;
   static constexpr int TOTAL = OFF_BAR + NBAR * 8 + 16 + 1024;
@@ -153,6 +156,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     fence_barrier_init();
   }
   if (warp == ATT_W_MMA) tmem_alloc<TMEM_COLS>(tmem_ptr_smem);
+  // bias window in shared memory: entries [b_lo, b_lo + b_len) of this head's vector cover every (row, key) of the CTA
+  [[maybe_unused]] const int n_rel_ = p.seq_q + p.seq_kv - 1;
+  [[maybe_unused]] const int b_lo = (p.seq_q - 1) - min(q0 + ATT_NQ * ATT_BQ - 1, p.seq_q - 1);
+  [[maybe_unused]] const int b_len = ATT_NQ * ATT_BQ + n_total * ATT_BKV;
+  constexpr bool kBiasSmem = kBias && kPT && NQ == 2;
+  [[maybe_unused]] const bool bias_in_smem = kBiasSmem && b_len <= S::BIAS_FLOATS;
+  if constexpr (kBiasSmem) {
+    if (bias_in_smem) {
+      float* bs = reinterpret_cast<float*>(smem + S::OFF_P);
+      const float* src = p.rel_bias + int64_t(head) * n_rel_ + b_lo;
+      for (int i = threadIdx.x; i < b_len; i += NQ * ATT_GROUP + 128)
+        bs[i] = (b_lo + i < n_rel_) ? __ldg(src + i) * 1.4426950408889634f : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -280,6 +297,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int n_rel = p.seq_q + p.seq_kv - 1;
     const float* brow = kBias ? p.rel_bias + int64_t(head) * n_rel + (p.seq_q - 1 - min(q_row, p.seq_q - 1)) : nullptr;
     const float sc_eff = kBias ? 1.f : sc;        // with a bias the scores are moved to the scaled log2 domain first
+    [[maybe_unused]] const int bias_k0 = (p.seq_q - 1 - min(q_row, p.seq_q - 1)) - b_lo;   // this row's offset into the smem window
 
     float m_ref = -INFINITY;                      // exponent reference, scaled log2 domain
     float l0 = 0.f, l1 = 0.f;                     // two partial row sums (shorter FADD chains)
@@ -311,7 +329,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int c0 = j * ATT_BKV;
       if constexpr (kBias) {
         constexpr float kLog2e = 1.4426950408889634f;
-        if (c0 + ATT_BKV <= p.seq_kv) {
+        if (bias_in_smem) {
+          // 64 consecutive window entries of this row (lanes walk the window backwards by one: conflict-free), already in
+          // log2 units; the window is zero-padded past the vector, so the ragged last tile needs no clamp
+          const float* bs = reinterpret_cast<const float*>(smem + S::OFF_P) + bias_k0 + c0;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) cur[c] = __float_as_uint(fmaf(__uint_as_float(cur[c]), sc, bs[c]));
+        } else if (c0 + ATT_BKV <= p.seq_kv) {
 #pragma unroll
           for (int c = 0; c < 64; ++c)
             cur[c] = __float_as_uint(fmaf(__ldg(brow + c0 + c), kLog2e, __uint_as_float(cur[c]) * sc));
