@@ -47,9 +47,15 @@ class ModelCheckpoint(Callback):
         if last:
             name = "last"
         else:
-            name = self.filename.replace("{epoch:02d}", f"{trainer.current_epoch:02d}") \
-                .replace("{step:d}", str(trainer.global_step)).replace("{epoch}", str(trainer.current_epoch)) \
-                .replace("{step}", str(trainer.global_step))
+            import re
+            vals = {k: (float(v) if hasattr(v, "__float__") else v) for k, v in trainer.callback_metrics.items()}
+            vals.update(epoch=trainer.current_epoch, step=trainer.global_step)
+
+            def fill(m):   # {epoch:02d}, {step:d}, {train_loss:.4f}, ... ; metrics not logged yet format as 0
+                v = vals.get(m.group(1), 0)
+                spec = m.group(2) or ""
+                return format(int(v) if spec.endswith("d") else v, spec)
+            name = re.sub(r"\{(\w+)(?::([^}]*))?\}", fill, self.filename)
         return os.path.join(self.dirpath or ".", name + ".ckpt")
 
     def on_train_batch_end(self, trainer, pl_module, outputs, batch, batch_idx):

@@ -255,7 +255,10 @@ class Trainer:
             int(getattr(getattr(self.datamodule, "hparams", {}), "train_batchsize", 1) or 1)
         if self.global_rank == 0:
             state = {"module": {k: v.detach().cpu() for k, v in module.state_dict().items()},
-                     "global_steps": self.global_step, "global_samples": consumed, "epoch": self.current_epoch,
+                     # DeepSpeed's own counters (global_steps / global_samples) next to PL's client state (global_step / epoch):
+                     # pretrain_erlangshen.py:192-197 reads checkpoint["global_step"], finetune_ziya_llama.py:180-183 'global_samples'
+                     "global_steps": self.global_step, "global_step": self.global_step, "global_samples": consumed,
+                     "epoch": self.current_epoch,
                      "lr_schedulers": [sc["scheduler"].state_dict() for sc in self.lr_scheduler_configs]}
             module.on_save_checkpoint(state)
             torch.save(state, os.path.join(ck, "mp_rank_00_model_states.pt"))
