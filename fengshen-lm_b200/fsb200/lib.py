@@ -16,7 +16,7 @@ c_i64 = ctypes.c_int64
 c_f32 = ctypes.c_float
 c_size = ctypes.c_size_t
 
-BF16, F32 = 0, 1
+BF16, F32, U32, U64 = 0, 1, 2, 3
 GEMM_NT, GEMM_NN, GEMM_TN = 0, 1, 2
 EPI_NONE, EPI_GELU_TANH, EPI_GELU_ERF = 0, 1, 2
 ACT_SILU, ACT_GELU_TANH, ACT_GELU_ERF, ACT_TANH = 0, 1, 2, 3
@@ -79,6 +79,12 @@ SIGNATURES = {
     "fsb_comm_reduce_scatter": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "fsb_comm_all_gather": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
     "fsb_comm_all_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p]),
+    "fsb_index_build_sample_idx": (c_int, [c_void_p, c_void_p, c_i64, ctypes.c_int32, ctypes.c_int32, c_i64, c_void_p, c_i64]),
+    "fsb_index_build_mapping": (c_i64, [c_void_p, c_i64, c_void_p, ctypes.c_int32, ctypes.c_uint64, ctypes.c_int32,
+                                        ctypes.c_double, ctypes.c_int32, ctypes.c_int32, c_int, c_void_p, c_i64]),
+    "fsb_index_build_blocks_mapping": (c_i64, [c_void_p, c_i64, c_void_p, c_void_p, ctypes.c_int32, ctypes.c_uint64,
+                                               ctypes.c_int32, ctypes.c_int32, c_int, c_int, c_void_p, c_i64]),
+    "fsb_index_build_blending_indices": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int32, c_i64]),
     "fsb_sdpa_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int,
                              c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_void_p, c_void_p,
                              c_void_p]),
@@ -124,7 +130,8 @@ def check(rc, what):
 kernel_launches = 0  # number of __global__ launches issued by the library on behalf of this process
 # kernels launched per successful entry-point call (everything not listed launches exactly one)
 _NO_KERNEL = {"fsb_set_reserved_sms", "fsb_comm_unique_id", "fsb_comm_init", "fsb_comm_destroy", "fsb_comm_reduce_scatter",
-              "fsb_comm_all_gather", "fsb_comm_all_reduce"}   # host-only calls / NCCL's kernels, not ours
+              "fsb_comm_all_gather", "fsb_comm_all_reduce", "fsb_index_build_sample_idx", "fsb_index_build_mapping",
+              "fsb_index_build_blocks_mapping", "fsb_index_build_blending_indices"}   # host-only calls / NCCL's kernels, not ours
 _KERNELS_PER_CALL = {"fsb_rmsnorm_bwd": 2, "fsb_layernorm_bwd": 2, "fsb_softmax_xent_fwd_bwd": 3, "fsb_sdpa_bwd": 3,
                      "fsb_sumsq": 2, "fsb_colsum": 2, "fsb_act_bwd_bias": 2}
 

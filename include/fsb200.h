@@ -33,7 +33,7 @@ typedef enum {
   FSB_ERR_UNSUPPORTED = -3  /* valid request this build does not implement */
 } fsb_status;
 
-typedef enum { FSB_BF16 = 0, FSB_F32 = 1 } fsb_dtype;
+typedef enum { FSB_BF16 = 0, FSB_F32 = 1, FSB_U32 = 2, FSB_U64 = 3 /* index builders only */ } fsb_dtype;
 
 /* ---- library ---------------------------------------------------------------------------------------------- */
 int fsb_version(void);               /* 1000*major + minor */
@@ -255,6 +255,34 @@ int fsb_comm_destroy(fsb_comm_t comm);
 int fsb_comm_reduce_scatter(fsb_comm_t comm, const void* send, void* recv, int64_t recv_count, int dtype, fsb_stream_t stream);
 int fsb_comm_all_gather(fsb_comm_t comm, const void* send, void* recv, int64_t send_count, int dtype, fsb_stream_t stream);
 int fsb_comm_all_reduce(fsb_comm_t comm, const void* send, void* recv, int64_t count, int dtype, fsb_stream_t stream);
+
+/* ---- index builders of the Megatron indexed datasets (HOST functions: no device, no stream) -----------------------
+ * Replace the pybind11 module `helpers` (fengshen/data/megatron_dataloader/helpers.cpp:788-793, built by its Makefile:1-9 and
+ * called from blendable_dataset.py:51 and dataset_utils.py). Integer outputs are bit-identical to the reference's, including its
+ * pseudo-random sequence (std::mt19937(seed) for the short-sequence draws, std::mt19937_64(seed + 1) for the row shuffle), so
+ * an index cached by one implementation is valid for the other. All arrays are caller-owned, C-contiguous.
+ *
+ * fsb_index_build_sample_idx  (helpers.cpp:101-195): GPT-style flattened stream. sizes[doc] = tokens per document, doc_idx
+ *   [n_doc_idx] = document order over all epochs. out: int32 [num_samples + 1, 2] rows (index into doc_idx, token offset), with
+ *   num_samples = (num_epochs * tokens_per_epoch - 1) / seq_length and out_rows == num_samples + 1.
+ * fsb_index_build_mapping     (helpers.cpp:213-516): BERT-style sentence spans. docs[n_docs + 1] = first sentence of each
+ *   document, sizes[sentence] = tokens. Rows (first sentence, end sentence, target length), dtype FSB_U32 or FSB_U64 (the
+ *   reference switches to uint64 when there are more than 2^32-1 sentences). Call with out == NULL to get the row count, then
+ *   with out_rows == that count; the filled rows are shuffled. Returns the row count, or -1 with fsb_last_error() set.
+ * fsb_index_build_blocks_mapping (helpers.cpp:518-786): as above with a per-document title length subtracted from the target and
+ *   rows (first sentence, end sentence, document, block id within the epoch).
+ * fsb_index_build_blending_indices (helpers.cpp:34-99): for `size` samples pick, greedily, the dataset whose sample count lags
+ *   its weight the most; dataset_index uint8 [size], dataset_sample_index int64 [size]. */
+int fsb_index_build_sample_idx(const int32_t* sizes, const int32_t* doc_idx, int64_t n_doc_idx, int32_t seq_length,
+                               int32_t num_epochs, int64_t tokens_per_epoch, int32_t* out, int64_t out_rows);
+int64_t fsb_index_build_mapping(const int64_t* docs, int64_t n_docs, const int32_t* sizes, int32_t num_epochs,
+                                uint64_t max_num_samples, int32_t max_seq_length, double short_seq_prob, int32_t seed,
+                                int32_t min_num_sent, int dtype, void* out, int64_t out_rows);
+int64_t fsb_index_build_blocks_mapping(const int64_t* docs, int64_t n_docs, const int32_t* sizes, const int32_t* titles_sizes,
+                                       int32_t num_epochs, uint64_t max_num_samples, int32_t max_seq_length, int32_t seed,
+                                       int use_one_sent_blocks, int dtype, void* out, int64_t out_rows);
+int fsb_index_build_blending_indices(uint8_t* dataset_index, int64_t* dataset_sample_index, const double* weights,
+                                     int32_t num_datasets, int64_t size);
 
 #ifdef __cplusplus
 }
