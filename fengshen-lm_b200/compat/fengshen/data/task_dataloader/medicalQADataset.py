@@ -1,8 +1,8 @@
-"""`GPT2QADataset` / `GPT2QADataModel` — the data side of the Wenzhong-GPT2 recipe (C2):
-fengshen/data/task_dataloader/medicalQADataset.py:9-124, imported by examples/wenzhong_qa/finetune_wenzhong.py:10. One Python
-dict literal per line with 'Question' and 'answer'; each item is question+answer tokenised, padded / truncated to
-max_seq_length, and the padding positions of `labels` set to -100. Same flags and constructor; lines are parsed with
-ast.literal_eval (the reference calls eval() on them)."""
+"""`GPT2QADataset` / `GPT2QADataModel` — the data side of the Wenzhong-GPT2 recipe (C2), restated from
+fengshen/data/task_dataloader/medicalQADataset.py:9-124 (imported by examples/wenzhong_qa/finetune_wenzhong.py:10): one Python
+dict literal per line with 'Question' and 'answer'; an item is question + answer tokenised, padded / truncated to max_seq_length,
+with the padding positions of `labels` set to -100. The flag names, defaults and constructor are the reference's (they are the
+schema its launch scripts pass); lines are parsed with ast.literal_eval where the reference calls eval()."""
 import ast
 import os
 
@@ -10,26 +10,31 @@ import pytorch_lightning as pl
 from torch.utils.data import DataLoader, Dataset
 from transformers import AutoTokenizer
 
+# (flag, keyword arguments of add_argument) — medicalQADataset.py:84-92
+_FLAGS = (
+    ('--data_dir', dict(type=str, required=True)),
+    ('--num_workers', dict(default=2, type=int)),
+    ('--train_data', dict(default='train.txt', type=str)),
+    ('--valid_data', dict(default='valid.txt', type=str)),
+    ('--test_data', dict(default='test.txt', type=str)),
+    ('--train_batchsize', dict(type=int, required=True)),
+    ('--valid_batchsize', dict(type=int, required=True)),
+    ('--max_seq_length', dict(default=1024, type=int)),
+)
+
 
 class GPT2QADataset(Dataset):
     def __init__(self, data_path, name, args):
         super().__init__()
-        self.tokenizer = AutoTokenizer.from_pretrained(args.pretrained_model_path)
-        if self.tokenizer.pad_token is None:
-            self.tokenizer.add_special_tokens({'pad_token': '<|endoftext|>'})
-        self.data_type_name = name
-        self.max_seq_length = args.max_seq_length
+        tok = AutoTokenizer.from_pretrained(args.pretrained_model_path)
+        if tok.pad_token is None:   # GPT-2 vocabularies have no padding token: the end-of-text token stands in
+            tok.add_special_tokens({'pad_token': '<|endoftext|>'})
+        self.tokenizer, self.data_type_name, self.max_seq_length = tok, name, args.max_seq_length
         self.data = self.load_data(data_path)
 
-    def __len__(self):
-        return len(self.data)
-
-    def __getitem__(self, index):
-        return self.encode(self.data[index])
-
     def load_data(self, data_path):
-        with open(data_path, "rt", encoding='utf8') as f:   # streamed; the reference's >5 GB branch differs only in its progress bar
-            return [self.data_parse(line) for line in f if line.strip()]
+        with open(data_path, "rt", encoding='utf8') as lines:
+            return [self.data_parse(line) for line in lines if line.strip()]
 
     def data_parse(self, line):
         return ast.literal_eval(line.strip())
@@ -37,36 +42,35 @@ class GPT2QADataset(Dataset):
     def encode(self, item):
         enc = self.tokenizer(item['Question'] + item['answer'], max_length=self.max_seq_length, padding='max_length',
                              truncation=True, return_tensors='pt')
-        ids = enc['input_ids']
-        labels = ids.clone().detach()
+        ids, mask = enc['input_ids'].squeeze(), enc['attention_mask'].squeeze()
+        labels = ids.clone()
         labels[ids == self.tokenizer.pad_token_id] = -100
-        return {"input_ids": ids.squeeze(), "attention_mask": enc['attention_mask'].squeeze(), "labels": labels.squeeze(),
-                "question": item['Question'], "answer": item['answer']}
+        return dict(input_ids=ids, attention_mask=mask, labels=labels, question=item['Question'], answer=item['answer'])
+
+    def __getitem__(self, index):
+        return self.encode(self.data[index])
+
+    def __len__(self):
+        return len(self.data)
 
 
 class GPT2QADataModel(pl.LightningDataModule):
     @staticmethod
     def add_data_specific_args(parent_args):
-        parser = parent_args.add_argument_group('GPT2QADataModel')
-        parser.add_argument('--data_dir', type=str, required=True)
-        parser.add_argument('--num_workers', default=2, type=int)
-        parser.add_argument('--train_data', default='train.txt', type=str)
-        parser.add_argument('--valid_data', default='valid.txt', type=str)
-        parser.add_argument('--test_data', default='test.txt', type=str)
-        parser.add_argument('--train_batchsize', type=int, required=True)
-        parser.add_argument('--valid_batchsize', type=int, required=True)
-        parser.add_argument('--max_seq_length', default=1024, type=int)
+        group = parent_args.add_argument_group('GPT2QADataModel')
+        for flag, kw in _FLAGS:
+            group.add_argument(flag, **kw)
         return parent_args
 
     def __init__(self, args):
         super().__init__()
         self.args = args
-        self.train_batchsize = args.train_batchsize
-        self.valid_batchsize = args.valid_batchsize
+        self.train_batchsize, self.valid_batchsize = args.train_batchsize, args.valid_batchsize
+        at = lambda name: os.path.join(args.data_dir, name)
         if not args.do_eval_only:
-            self.train_data = GPT2QADataset(os.path.join(args.data_dir, args.train_data), '训练集', args)
-            self.valid_data = GPT2QADataset(os.path.join(args.data_dir, args.valid_data), '验证集', args)
-        self.test_data = GPT2QADataset(os.path.join(args.data_dir, args.test_data), '测试集', args)
+            self.train_data = GPT2QADataset(at(args.train_data), '训练集', args)
+            self.valid_data = GPT2QADataset(at(args.valid_data), '验证集', args)
+        self.test_data = GPT2QADataset(at(args.test_data), '测试集', args)
 
     def _loader(self, ds, bs, shuffle):
         return DataLoader(ds, shuffle=shuffle, batch_size=bs, pin_memory=False, num_workers=self.args.num_workers)

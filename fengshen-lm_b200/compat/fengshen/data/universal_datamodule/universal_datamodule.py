@@ -21,24 +21,30 @@ def get_consume_samples(data_model):
 
 
 class UniversalDataModule(LightningDataModule):
+    # (flag, add_argument keywords) — universal_datamodule.py:22-46: the schema the launch scripts pass
+    _FLAGS = (
+        ('--num_workers', dict(default=8, type=int)),
+        ('--dataloader_workers', dict(default=2, type=int)),
+        ('--train_batchsize', dict(default=16, type=int)),
+        ('--val_batchsize', dict(default=16, type=int)),
+        ('--test_batchsize', dict(default=16, type=int)),
+        ('--datasets_name', dict(type=str, default=None)),
+        ('--train_datasets_field', dict(type=str, default='train')),
+        ('--val_datasets_field', dict(type=str, default='validation')),
+        ('--test_datasets_field', dict(type=str, default='test')),
+        ('--train_file', dict(type=str, default=None)),
+        ('--val_file', dict(type=str, default=None)),
+        ('--test_file', dict(type=str, default=None)),
+        ('--raw_file_type', dict(type=str, default='json')),
+        ('--sampler_type', dict(type=str, choices=['single', 'random'], default='random')),
+        ('--use_mpu', dict(action="store_true", default=False)),
+    )
+
     @staticmethod
     def add_data_specific_args(parent_args):
-        parser = parent_args.add_argument_group('Universal DataModule')
-        parser.add_argument('--num_workers', default=8, type=int)
-        parser.add_argument('--dataloader_workers', default=2, type=int)
-        parser.add_argument('--train_batchsize', default=16, type=int)
-        parser.add_argument('--val_batchsize', default=16, type=int)
-        parser.add_argument('--test_batchsize', default=16, type=int)
-        parser.add_argument('--datasets_name', type=str, default=None)
-        parser.add_argument('--train_datasets_field', type=str, default='train')
-        parser.add_argument('--val_datasets_field', type=str, default='validation')
-        parser.add_argument('--test_datasets_field', type=str, default='test')
-        parser.add_argument('--train_file', type=str, default=None)
-        parser.add_argument('--val_file', type=str, default=None)
-        parser.add_argument('--test_file', type=str, default=None)
-        parser.add_argument('--raw_file_type', type=str, default='json')
-        parser.add_argument('--sampler_type', type=str, choices=['single', 'random'], default='random')
-        parser.add_argument('--use_mpu', action="store_true", default=False)
+        group = parent_args.add_argument_group('Universal DataModule')
+        for flag, kw in UniversalDataModule._FLAGS:
+            group.add_argument(flag, **kw)
         return parent_args
 
     def __init__(self, tokenizer, collate_fn, args, datasets=None, **kwargs):
