@@ -49,3 +49,85 @@ def test_erlangshen_recipe_host_flow(launched_with_doubles, tmp_path, monkeypatc
 
 def test_wenzhong_recipe_host_flow(launched_with_doubles, tmp_path):
     R.wenzhong_recipe(tmp_path, min_drop=0.02, device="cpu")
+
+
+# ---- two data-parallel ranks over gloo: sharded optimizer state, per-rank sample streams, two optimizer-shard files, resume ----
+def _rank_main(rank, world, port, workdir, q):
+    import json
+    import runpy
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port), PL_DEEPSPEED_CONFIG_PATH=os.path.join(workdir, "ds_config.json"))
+    sys.path.insert(0, os.path.join(F.ROOT, "tests"))
+    sys.path.insert(0, os.path.join(F.ROOT, "fengshen-lm_b200"))
+    import torch
+    import cpu_kernels
+    import fsb200.engine as engine
+    import fsb200.hf as hf
+    import fsb200.launch as launch
+    import toy_models as T
+
+    class CpuEngine(engine.ZeroEngine):
+        def __init__(self, model, **kw):
+            kw.setdefault("kernels", cpu_kernels)
+            super().__init__(model, **kw)
+
+    engine.ZeroEngine = CpuEngine
+    hf.MegatronBertForPreTraining = type("MegatronBertForPreTraining", (hf._HFSurface, T.ToyMegatronBert),
+                                         {"config_name": "MegatronBertConfig"})
+    launch.prepare(R.EXAMPLE)
+    ns = runpy.run_path(R.EXAMPLE, run_name="example_not_main")
+
+    def argv(epochs):
+        return ["--model_path", os.path.join(workdir, "m"), "--train_file", os.path.join(workdir, "train.json"),
+                "--train_batchsize", "4", "--max_seq_length", "64", "--max_epoch", str(epochs), "--learning_rate", "2e-2",
+                "--strategy", "deepspeed_stage_1", "--replace_sampler_ddp", "False", "--dataloader_workers", "0",
+                "--log_every_n_steps", "1", "--default_root_dir", workdir, "--save_ckpt_path", os.path.join(workdir, "ckpt"),
+                "--load_ckpt_path", os.path.join(workdir, "ckpt", "last.ckpt"), "--save_last", "--precision", "bf16"]
+
+    trainer, module = ns["main"](argv(1))
+    first = (trainer.global_step, trainer.engine.world, module.model.flat.world_size, module.model.flat.params.float().numpy().copy())
+    trainer2, module2 = ns["main"](argv(2))
+    q.put((rank, first, (trainer2.global_step, getattr(module2, "consumed_samples", None),
+                         module2.model.flat.params.float().numpy().copy())))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_erlangshen_recipe_two_ranks_over_gloo(tmp_path):
+    import json
+    import numpy as np
+    import torch
+    import torch.multiprocessing as mp
+    F.bert_dir(tmp_path / "m")
+    F.bert_corpus(tmp_path / "train.json", n=64)
+    (tmp_path / "ds_config.json").write_text(json.dumps({"zero_optimization": {"stage": 1}, "bf16": {"enabled": True},
+                                                         "gradient_clipping": 2, "train_micro_batch_size_per_gpu": 4}))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, 29655, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        got = {}
+        for _ in range(2):
+            rank, first, second = q.get(timeout=240)
+            got[rank] = (first, second)
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.terminate()
+    assert all(p.exitcode == 0 for p in procs)
+    for rank in (0, 1):
+        (steps, eng_world, flat_world, _), (steps2, consumed, _) = got[rank]
+        assert (steps, eng_world, flat_world) == (8, 2, 2)            # 64 documents / (4 per rank x 2 ranks)
+        assert steps2 == 16 and consumed == 64                        # resumed: 8 + 8 steps, sample counter from the checkpoint
+    assert np.array_equal(got[0][0][3], got[1][0][3]) and np.array_equal(got[0][1][2], got[1][1][2])   # ranks agree after all-gather
+    assert not np.array_equal(got[0][0][3], got[0][1][2])
+    ck = tmp_path / "ckpt" / "last.ckpt" / "checkpoint"
+    assert sorted(os.listdir(ck)) == ["mp_rank_00_model_states.pt", "zero_pp_rank_0_mp_rank_00_optim_states.pt",
+                                      "zero_pp_rank_1_mp_rank_00_optim_states.pt"]
+    state = torch.load(ck / "mp_rank_00_model_states.pt", map_location="cpu", weights_only=False)
+    assert state["global_step"] == 16 and state["global_samples"] == 128
+    shard = torch.load(ck / "zero_pp_rank_1_mp_rank_00_optim_states.pt", map_location="cpu", weights_only=False)
+    assert shard["format"] == "fsb200-zero-shard-v1"

@@ -25,7 +25,10 @@ class _ToyBase(nn.Module):
         super().__init__()
         self.config = config
         self.V = config.vocab_size
-        self.flat = FlatBuffers(self._spec(self.V, self.H), "cpu", world_size=world_size or 1)
+        if world_size is None:   # as the real models: the initialised process group decides
+            import torch.distributed as dist
+            world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.flat = FlatBuffers(self._spec(self.V, self.H), "cpu", world_size=world_size)
         self._p = {}
         g = torch.Generator().manual_seed(seed)
         for name, (_, shape) in self.flat.offsets.items():
