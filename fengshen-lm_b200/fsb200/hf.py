@@ -120,6 +120,8 @@ def install():
             if cur is not g[n]:
                 _originals.setdefault(n, cur)
                 setattr(mod, n, g[n])
+        if not hasattr(mod, "MT5Tokenizer"):   # removed in transformers 5.x, where it was `MT5Tokenizer = T5Tokenizer`;
+            mod.MT5Tokenizer = mod.T5Tokenizer   # pretrain_t5.py:9 imports it by that name
 
 
 def uninstall():

@@ -46,6 +46,16 @@ def main():
         rec[f"{name}_raw"] = raw
         for k in ("input_ids", "labels", "decoder_input_ids"):
             rec[f"{name}_{k}"] = out[k].numpy().astype(np.int64)
+    # group_texts (t5_datasets.py:160-177) called unbound on a stand-in `self` that carries the one attribute it reads
+    from types import SimpleNamespace
+    rs = np.random.RandomState(3)
+    for name, (chunk, n_rows) in {"g1": (16, 40), "g2": (568, 9), "g3": (50, 2)}.items():
+        rows = [rs.randint(0, 1000, size=int(rs.randint(0, 60))).tolist() for _ in range(n_rows)]
+        got = mod.UnsuperviseT5Dataset.group_texts(SimpleNamespace(expanded_inputs_length=chunk), {"input_ids": rows})
+        rec[f"{name}_rows"] = np.array([len(r) for r in rows] + [chunk], dtype=np.int64)
+        rec[f"{name}_flat"] = np.array([t for r in rows for t in r], dtype=np.int64)
+        rec[f"{name}_lens"] = np.array([len(c) for c in got["input_ids"]], dtype=np.int64)
+        rec[f"{name}_out"] = np.array([t for c in got["input_ids"] for t in c], dtype=np.int64)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "t5_collator.npz"), **rec)
     print({k: v.shape for k, v in rec.items()})
 

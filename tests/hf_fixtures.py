@@ -69,3 +69,36 @@ def qa_files(data_dir, n=48):
             for r in rows:
                 f.write(repr(r) + "\n")
     return rows
+
+
+MT5_CFG = {"model_type": "mt5", "vocab_size": 512, "d_model": 256, "d_kv": 64, "d_ff": 512, "num_layers": 2,
+           "num_decoder_layers": 2, "num_heads": 4, "relative_attention_num_buckets": 32, "dropout_rate": 0.0,
+           "feed_forward_proj": "gated-gelu", "pad_token_id": 0, "eos_token_id": 1, "decoder_start_token_id": 0,
+           "tie_word_embeddings": True}
+
+
+def t5_dir(path):
+    """mT5 directory for the `bert_tokenizer` branch of pretrain_t5.py: config.json + vocab.txt."""
+    import bert_collator_cases as C
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "vocab.txt"), "w", encoding="utf8") as f:
+        f.write("\n".join(C.build_vocab()) + "\n")
+    with open(os.path.join(path, "config.json"), "w") as f:
+        json.dump(MT5_CFG, f)
+
+
+def t5_tokenised_dir(path, n_train=48, n_test=8, length=70, vocab=400, seed=0):
+    """A `datasets.save_to_disk` directory with 'train' / 'test' splits of already tokenised chunks: `input_ids` of the expanded
+    length for max_seq_length 64 (compute_input_and_target_lengths(64, .15, 3) = (70, 14))."""
+    import datasets
+    import numpy as np
+    rs = np.random.RandomState(seed)
+    # a learnable stream: every chunk repeats a short motif, so that the span targets are predictable from the inputs
+    def rows(n):
+        out = []
+        for _ in range(n):
+            motif = rs.randint(5, vocab, size=4)
+            out.append(np.tile(motif, length // 4 + 1)[:length].tolist())
+        return out
+    datasets.DatasetDict({"train": datasets.Dataset.from_dict({"input_ids": rows(n_train)}),
+                          "test": datasets.Dataset.from_dict({"input_ids": rows(n_test)})}).save_to_disk(str(path))

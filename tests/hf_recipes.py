@@ -147,3 +147,107 @@ def wenzhong_recipe(tmp_path, min_drop, device):
         l2 = model.model(input_ids=dev(ids2), attention_mask=dev(b['attention_mask']), labels=dev(b['labels'])).loss
     assert abs(float(l1) - float(l2)) < 1e-3
     return trainer, model
+
+
+def t5_recipe(tmp_path, min_drop, lr="2e-3"):
+    """pretrain_t5.py:16-155 in miniature (its `bert_tokenizer` branch: model from MT5Config, no pretrained weights): the compat
+    UnsuperviseT5DataModel over a tokenised `datasets` directory (span corruption in the collate step, Megatron sampler), the
+    module's own total-step arithmetic, fengshen.models.model_utils.configure_optimizers, on_save_checkpoint exporting
+    `hf_pretrained_epoch{}_step{}` next to the checkpoints, then a resumed second epoch."""
+    import argparse
+    import pytorch_lightning as pl
+    from pytorch_lightning import Trainer, loggers
+    from pytorch_lightning.callbacks import LearningRateMonitor
+    from transformers import MT5Config, MT5ForConditionalGeneration
+    from fengshen.data.t5_dataloader.t5_datasets import UnsuperviseT5DataModel
+    from fengshen.models.model_utils import add_module_args, configure_optimizers
+    from fengshen.utils.universal_checkpoint import UniversalCheckpoint
+    assert not MT5ForConditionalGeneration.__module__.startswith("transformers.")
+    F.t5_dir(tmp_path / "m")
+    F.t5_tokenised_dir(tmp_path / "tok")
+
+    class MT5PretrainModel(pl.LightningModule):
+        def __init__(self, args):
+            super().__init__()
+            self.save_hyperparameters(args)
+            self.model = MT5ForConditionalGeneration(MT5Config.from_pretrained(args.pretrained_model_path))
+
+        def setup(self, stage) -> None:
+            if stage == 'fit':
+                train_loader = self.trainer._data_connector._train_dataloader_source.dataloader()
+                tb_size = self.hparams.train_batchsize * max(1, self.trainer.world_size)
+                ab_size = self.trainer.accumulate_grad_batches * float(self.trainer.max_epochs)
+                self.total_steps = (len(train_loader.dataset) * self.trainer.max_epochs // tb_size) // ab_size
+
+        def configure_optimizers(self):
+            return configure_optimizers(self)
+
+        def training_step(self, batch, batch_idx):
+            output = self.model(input_ids=batch['input_ids'], labels=batch['labels'])
+            y_pred = torch.argmax(output.logits, dim=-1).view(size=(-1,))
+            y_true = batch['labels'].view(size=(-1,)).float()
+            self.log('train_loss', output.loss, sync_dist=True)
+            self.log('train_acc', torch.sum(torch.eq(y_pred, y_true).float()) / y_true.shape[0], sync_dist=True)
+            return output.loss
+
+        def on_save_checkpoint(self, checkpoint) -> None:
+            if self.trainer.global_rank == 0 and self.trainer.global_step % self.hparams.every_n_train_steps == 0:
+                self.model.save_pretrained(os.path.join(
+                    self.trainer.checkpoint_callback.dirpath,
+                    'hf_pretrained_epoch{}_step{}'.format(self.trainer.current_epoch, self.trainer.global_step)))
+
+        def on_load_checkpoint(self, checkpoint) -> None:
+            if 'global_samples' in checkpoint:
+                self.consumed_samples = checkpoint['global_samples']
+            self.trainer.fit_loop.epoch_loop._batches_that_stepped = checkpoint["global_step"]
+
+    def run(max_steps):
+        p = argparse.ArgumentParser("Pretrain Unsupervise.")
+        p.add_argument('--pretrained_model_path', default=None, type=str)
+        p.add_argument('--new_vocab_path', default=None, type=str)
+        p.add_argument('--max_seq_length', default=1024, type=int)
+        p.add_argument('--ckpt_path', default=None, type=str)
+        p = add_module_args(p)       # the flags model_utils.configure_optimizers reads (the reference script omits this call)
+        p = UnsuperviseT5DataModel.add_data_specific_args(p)
+        p = Trainer.add_argparse_args(p)
+        p = UniversalCheckpoint.add_argparse_args(p)
+        args = p.parse_args(["--pretrained_model_path", str(tmp_path / "m"), "--tokenizer_type", "bert_tokenizer",
+                             "--train_data_path", str(tmp_path / "tok"), "--train_split_size", "0.999", "--max_seq_length", "64",
+                             "--train_batchsize", "4", "--valid_batchsize", "4", "--dataloader_num_workers", "0",
+                             "--max_epochs", "1", "--max_steps", str(max_steps), "--learning_rate", lr, "--warmup_ratio", "0.1",
+                             "--strategy", "deepspeed_stage_2", "--log_every_n_steps", "1", "--default_root_dir", str(tmp_path),
+                             "--save_ckpt_path", str(tmp_path / "ckpt"), "--load_ckpt_path", str(tmp_path / "ckpt" / "last.ckpt"),
+                             "--every_n_train_steps", "6", "--save_last", "--precision", "bf16"])
+        data_model = UnsuperviseT5DataModel(args)
+        assert (data_model.expanded_inputs_length, data_model.targets_length) == (70, 14)
+        model = MT5PretrainModel(args)
+        logger = loggers.TensorBoardLogger(save_dir=os.path.join(args.default_root_dir, 'logs/'))
+        trainer = Trainer.from_argparse_args(args, logger=logger,
+                                             callbacks=[UniversalCheckpoint(args), LearningRateMonitor(logging_interval='step')])
+        trainer.fit(model, data_model, ckpt_path=args.load_ckpt_path)
+        return trainer, model, data_model
+
+    trainer, model, dm = run(6)                                                  # half of the epoch (48 chunks / 4 = 12 steps)
+    assert trainer.global_step == 6 and trainer.engine.stage == 2
+    losses = losses_of(trainer)
+    assert len(losses) == 6 and all(l == l for l in losses)
+    if min_drop is not None:
+        assert sum(losses[-2:]) / 2 < sum(losses[:2]) / 2 - min_drop, losses
+    batch = next(iter(dm.val_dataloader()))
+    assert batch["input_ids"].shape == (4, 64) and batch["labels"].shape == (4, 14)
+    assert (batch["input_ids"][:, -1] == 1).all() and (batch["input_ids"] >= 512 - 8).any()      # EOS last, sentinels present
+    exported = sorted(d for d in os.listdir(tmp_path / "ckpt") if d.startswith("hf_pretrained"))
+    assert exported == ["hf_pretrained_epoch0_step6"], exported
+    again = MT5ForConditionalGeneration.from_pretrained(str(tmp_path / "ckpt" / exported[0]))
+    assert torch.equal(again.state_dict()["shared.weight"], model.model.state_dict()["shared.weight"])
+    # the rest of the epoch from last.ckpt: the Megatron sampler continues behind the 24 consumed chunks
+    seen = []
+    orig = UnsuperviseT5DataModel.collate_fn
+    UnsuperviseT5DataModel.collate_fn = lambda self, ex: (seen.append([e["input_ids"][:4] for e in ex]), orig(self, ex))[1]
+    try:
+        trainer2, model2, dm2 = run(-1)
+    finally:
+        UnsuperviseT5DataModel.collate_fn = orig
+    assert trainer2.global_step == 12 and model2.consumed_samples == 24
+    assert len(seen) == 6 and seen[0][0] == dm2.train_dataset[24]["input_ids"][:4]
+    return trainer2, model2

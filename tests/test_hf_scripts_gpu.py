@@ -36,3 +36,9 @@ def test_erlangshen_recipe_trains_checkpoints_and_resumes(launched, tmp_path, mo
 def test_wenzhong_recipe_structure_trains(launched, tmp_path):
     trainer, module = R.wenzhong_recipe(tmp_path, min_drop=1.0, device="cuda")     # 48 near-identical rows: memorised quickly
     assert type(module.model).__module__ == "fsb200.hf" and module.model.flat.params.is_cuda
+
+
+def test_t5_recipe_structure_trains_exports_and_resumes_mid_epoch(launched, tmp_path):
+    # transformers' MT5ForConditionalGeneration on CPU with the same data / lr: 135 -> ~36 over the first 6 steps
+    trainer, module = R.t5_recipe(tmp_path, min_drop=10.0)
+    assert type(module.model).__module__ == "fsb200.hf" and module.model.flat.params.is_cuda

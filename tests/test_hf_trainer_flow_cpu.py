@@ -131,3 +131,14 @@ def test_erlangshen_recipe_two_ranks_over_gloo(tmp_path):
     assert state["global_step"] == 16 and state["global_samples"] == 128
     shard = torch.load(ck / "zero_pp_rank_1_mp_rank_00_optim_states.pt", map_location="cpu", weights_only=False)
     assert shard["format"] == "fsb200-zero-shard-v1"
+
+
+def test_t5_recipe_host_flow(launched_with_doubles, tmp_path, monkeypatch):
+    import fsb200.hf as hf
+    import toy_models as T
+    import transformers
+    toy = type("MT5ForConditionalGeneration", (hf._HFSurface, T.ToyMT5), {"config_name": "MT5Config"})
+    monkeypatch.setattr(hf, "MT5ForConditionalGeneration", toy)
+    hf.install()
+    assert transformers.MT5Tokenizer is transformers.T5Tokenizer                # the alias transformers 4.x shipped
+    R.t5_recipe(tmp_path, min_drop=None, lr="2e-2")

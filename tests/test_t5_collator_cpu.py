@@ -52,3 +52,20 @@ def test_noise_mask_properties_and_ragged_input_is_rejected():
     coll = T5SpanCorruptionCollator(vocab_size=1000, max_seq_length=64)
     with pytest.raises(ValueError, match="incorrectly preprocessed"):
         coll([{"input_ids": np.arange(2, 2 + 40)}])                               # wrong raw length: loud, like the reference
+
+
+def test_group_texts_matches_reference():
+    """The chunking step in front of the collator (t5_datasets.py:160-177), golden from the unmodified reference function."""
+    from fengshen.data.t5_dataloader.t5_datasets import group_texts
+    g = np.load(os.path.join(ROOT, "tests", "golden", "t5_collator.npz"))
+    for name in ("g1", "g2", "g3"):
+        lens, chunk = g[f"{name}_rows"][:-1], int(g[f"{name}_rows"][-1])
+        flat = g[f"{name}_flat"].tolist()
+        rows, k = [], 0
+        for n in lens:
+            rows.append(flat[k:k + n]); k += n
+        out = group_texts({"input_ids": rows}, chunk)["input_ids"]
+        assert [len(c) for c in out] == g[f"{name}_lens"].tolist()
+        assert [t for c in out for t in c] == g[f"{name}_out"].tolist()
+    assert g["g2_lens"].tolist() == [int(g["g2_rows"][:-1].sum())] and g["g2_lens"][0] < 568    # the short-batch branch
+    assert g["g3_lens"].tolist() == [50, 50] and g["g3_rows"][:-1].sum() == 113                 # tail of 13 tokens dropped

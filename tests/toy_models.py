@@ -42,6 +42,10 @@ class _ToyBase(nn.Module):
                     setattr(mod, part, _Holder())
                 mod = getattr(mod, part)
             setattr(mod, parts[-1], prm)
+        with torch.no_grad():
+            for name, prm in self._p.items():
+                if name.endswith("layer_norm.weight"):
+                    prm.fill_(1.0)
         self._gviews = {name: self.flat.view(name, grad=True) for name in self.flat.offsets}
         self.accumulate_grads, self.loss_scale, self.grad_hook = False, 1.0, None
 
@@ -160,4 +164,28 @@ class ToyGPT2(_ToyBase):
         if batch.get("labels") is not None:
             loss = nn.functional.cross_entropy(logits[:, :-1].reshape(-1, self.V), batch["labels"][:, 1:].reshape(-1),
                                                ignore_index=-100)
+        return loss, logits
+
+
+class ToyMT5(_ToyBase):
+    """Decoder token + mean encoder embedding -> tied output projection (keys named as in mT5 with a tied head)."""
+
+    def _spec(self, V, h):
+        s = FlatSpec()
+        s.add("shared.weight", (V, h), "shared")
+        s.add("decoder.final_layer_norm.weight", (h,), "head")
+        return s
+
+    def _loss(self, w, batch):
+        E = w["shared.weight"]
+        labels = batch.get("labels")
+        dec = batch.get("decoder_input_ids")
+        if dec is None:
+            dec = torch.zeros_like(labels)
+            dec[:, 1:] = labels[:, :-1]
+            dec = dec.masked_fill(dec == -100, 0)
+        hid = (E[dec] + E[batch["input_ids"]].mean(1, keepdim=True)) * w["decoder.final_layer_norm.weight"]
+        logits = hid @ E.t()
+        loss = None if labels is None else nn.functional.cross_entropy(logits.view(-1, self.V), labels.reshape(-1),
+                                                                      ignore_index=-100)
         return loss, logits
