@@ -59,3 +59,20 @@ def test_ops_refuse_cpu_tensors_loudly():
     a = torch.zeros(8, 8, dtype=torch.bfloat16)
     with pytest.raises(RuntimeError, match="CUDA"):
         ops.gemm(L.GEMM_NT, a, a)
+
+
+def test_plain_c_client_compiles_against_the_header_and_runs(tmp_path):
+    """include/fsb200.h is C (C99, -Wall -Wextra -Werror) and the library is usable without Python / torch: tests/c_abi_client.c
+    calls the host entry points (version, error string, index builders, the argument-validation path of a device entry point)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    from fsb200 import lib
+    libdir = os.path.dirname(lib.LIB_PATH)
+    exe = str(tmp_path / "c_abi_client")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi_client.c"), "-o", exe, "-L", libdir, "-lfsb200", f"-Wl,-rpath,{libdir}"],
+                   check=True, capture_output=True, text=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True, timeout=60)
+    assert "c_abi_client ok" in out.stdout
