@@ -63,3 +63,60 @@ class ErLangShenCollator:
         batch = {k: torch.stack([r[k] for r in rows]) for k in ('input_ids', 'attention_mask', 'token_type_ids', 'labels')}
         batch['next_sentence_label'] = torch.tensor([r['next_sentence_label'] for r in rows], dtype=torch.int64)
         return batch
+
+
+class FastErLangShenCollator(ErLangShenCollator):
+    """Same batches as `ErLangShenCollator`, with everything after tokenisation done by one C call (`fsb_bert_collate` in
+    libfsb200.so: segments, truncation, token types, whole-word n-gram masking, padding) on the collator's own numpy generator:
+    the rows AND the state `np_rng` is left in are bit-identical to the Python path (tests/test_bert_collator_cpu.py), so the
+    two can be swapped mid-run. Use it when the Python collator would limit the step (about 50 k tokens/s per core)."""
+
+    def setup(self):
+        super().setup()
+        import ctypes
+        from fsb200 import lib as L
+        self._L, self._ct = L, ctypes
+        L.load()
+        table = np.zeros(max(self.vocab_id_to_token_dict) + 1, dtype=np.uint8)
+        for i, piece in self.vocab_id_to_token_dict.items():
+            table[i] = piece.startswith("##")
+        self._continuation = table
+        # numpy's choice(p=...) arithmetic for n-gram sizes 1..3 (mask_utils.py:137-143 and :165-167), done by numpy itself
+        p = 1. / np.arange(1, 4)
+        p /= p.sum(keepdims=True)
+        p = p / p.sum(keepdims=True)
+        cdf = p.cumsum()
+        cdf /= cdf[-1]
+        self._ngram_cdf = np.ascontiguousarray(cdf, dtype=np.float64)
+
+    def _ragged(self, samples):
+        tk = self.tokenizer
+        flat, sent_off, doc_off = [], [0], [0]
+        for s in samples:
+            for sent in self.sentence_split.tokenize(s[self.content_key]):
+                flat.extend(tk.convert_tokens_to_ids(tk.tokenize(sent)))
+                sent_off.append(len(flat))
+            doc_off.append(len(sent_off) - 1)
+        return (np.asarray(flat, dtype=np.int32), np.asarray(sent_off, dtype=np.int64), np.asarray(doc_off, dtype=np.int64))
+
+    def __call__(self, samples):
+        tk, L_, ct = self.tokenizer, self.max_seq_length, self._ct
+        tokens, sent_off, doc_off = self._ragged(samples)
+        n_docs = len(samples)
+        vocab_ids = np.asarray(self.vocab_id_list, dtype=np.int32)
+        name, key, pos, has_gauss, cached = self.np_rng.get_state()
+        key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+        pos_c = ct.c_int32(int(pos))
+        out = [np.empty((n_docs, L_), dtype=np.int64) for _ in range(4)]
+        nsl = np.empty(n_docs, dtype=np.int64)
+        ptr = lambda a: ct.c_void_p(a.ctypes.data)
+        rows = self._L.load().fsb_bert_collate(
+            ptr(tokens), ptr(sent_off), ptr(doc_off), n_docs, ptr(self._continuation), self._continuation.shape[0],
+            ptr(vocab_ids), vocab_ids.shape[0], tk.cls_token_id, tk.sep_token_id, tk.mask_token_id, tk.pad_token_id, L_,
+            float(self.masked_lm_prob), ptr(self._ngram_cdf), 3, ptr(key), ct.byref(pos_c), *(ptr(a) for a in out), ptr(nsl))
+        if rows < 0:
+            raise RuntimeError(f"fsb200: fsb_bert_collate failed: {self._L.last_error()}")
+        self.np_rng.set_state((name, key, int(pos_c.value), has_gauss, cached))
+        ids, am, tt, lab = (torch.from_numpy(a[:rows]) for a in out)
+        return {'input_ids': ids, 'attention_mask': am, 'token_type_ids': tt, 'labels': lab,
+                'next_sentence_label': torch.from_numpy(nsl[:rows])}

@@ -85,6 +85,8 @@ SIGNATURES = {
     "fsb_index_build_blocks_mapping": (c_i64, [c_void_p, c_i64, c_void_p, c_void_p, ctypes.c_int32, ctypes.c_uint64,
                                                ctypes.c_int32, ctypes.c_int32, c_int, c_int, c_void_p, c_i64]),
     "fsb_index_build_blending_indices": (c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int32, c_i64]),
+    "fsb_bert_collate": (c_i64, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64] + [ctypes.c_int32] * 5 +
+                         [ctypes.c_double, c_void_p, ctypes.c_int32, c_void_p, c_void_p] + [c_void_p] * 5),
     "fsb_sdpa_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_int, c_int,
                              c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_f32, c_int, c_void_p, c_void_p,
                              c_void_p]),
@@ -131,7 +133,7 @@ kernel_launches = 0  # number of __global__ launches issued by the library on be
 # kernels launched per successful entry-point call (everything not listed launches exactly one)
 _NO_KERNEL = {"fsb_set_reserved_sms", "fsb_comm_unique_id", "fsb_comm_init", "fsb_comm_destroy", "fsb_comm_reduce_scatter",
               "fsb_comm_all_gather", "fsb_comm_all_reduce", "fsb_index_build_sample_idx", "fsb_index_build_mapping",
-              "fsb_index_build_blocks_mapping", "fsb_index_build_blending_indices"}   # host-only calls / NCCL's kernels, not ours
+              "fsb_index_build_blocks_mapping", "fsb_index_build_blending_indices", "fsb_bert_collate"}   # host-only calls / NCCL's kernels, not ours
 _KERNELS_PER_CALL = {"fsb_rmsnorm_bwd": 2, "fsb_layernorm_bwd": 2, "fsb_softmax_xent_fwd_bwd": 3, "fsb_sdpa_bwd": 3,
                      "fsb_sumsq": 2, "fsb_colsum": 2, "fsb_act_bwd_bias": 2}
 

@@ -284,6 +284,25 @@ int64_t fsb_index_build_blocks_mapping(const int64_t* docs, int64_t n_docs, cons
 int fsb_index_build_blending_indices(uint8_t* dataset_index, int64_t* dataset_sample_index, const double* weights,
                                      int32_t num_datasets, int64_t size);
 
+/* ---- MegatronBERT sample assembly (HOST function) --------------------------------------------------------------------
+ * The per-document work of `ErLangShenCollator` (fengshen/examples/pretrain_erlangshen_bert/pretrain_erlangshen.py:57-123 ->
+ * data_utils/sop_utils.py:2-32, truncate_utils.py:2-19, token_type_utils.py:1-25, mask_utils.py:19-285 with its defaults:
+ * whole-word n-gram masking, 'bert' style) over a batch of TOKENISED documents:
+ *   tokens[sent_offsets[s] .. sent_offsets[s+1]) is sentence s; document d holds sentences [doc_offsets[d], doc_offsets[d+1]).
+ * continuation[id] != 0 marks WordPiece continuation pieces ("##..."); vocab_ids[n_vocab_ids] is the list random replacements are
+ * drawn from; ngram_cdf[max_ngrams] the normalised cumulative weights of n-gram sizes 1..max_ngrams as numpy computes them
+ * (cumsum(p) / cumsum(p)[-1] with p ~ 1/n).
+ * mt_key[624] / mt_pos are numpy's legacy MT19937 state (`RandomState.get_state()[1:3]`), read and UPDATED: the rows and the state
+ * left behind are bit-identical to running the Python collator on the same generator.
+ * Outputs are int64 [n_docs, max_seq_length] (next_sentence_label: [n_docs]); documents that yield no sample (no sentence, empty
+ * first segment) are skipped, the return value is the number of rows written (-1 + fsb_last_error() on a bad argument). */
+int64_t fsb_bert_collate(const int32_t* tokens, const int64_t* sent_offsets, const int64_t* doc_offsets, int64_t n_docs,
+                         const uint8_t* continuation, int64_t vocab_table_len, const int32_t* vocab_ids, int64_t n_vocab_ids,
+                         int32_t cls_id, int32_t sep_id, int32_t mask_id, int32_t pad_id, int32_t max_seq_length,
+                         double masked_lm_prob, const double* ngram_cdf, int32_t max_ngrams, uint32_t* mt_key, int32_t* mt_pos,
+                         int64_t* input_ids, int64_t* attention_mask, int64_t* token_type_ids, int64_t* labels,
+                         int64_t* next_sentence_label);
+
 #ifdef __cplusplus
 }
 #endif
