@@ -82,7 +82,8 @@ def _rank_main(rank, world, port, workdir, q):
                 "--train_batchsize", "4", "--max_seq_length", "64", "--max_epoch", str(epochs), "--learning_rate", "2e-2",
                 "--strategy", "deepspeed_stage_1", "--replace_sampler_ddp", "False", "--dataloader_workers", "0",
                 "--log_every_n_steps", "1", "--default_root_dir", workdir, "--save_ckpt_path", os.path.join(workdir, "ckpt"),
-                "--load_ckpt_path", os.path.join(workdir, "ckpt", "last.ckpt"), "--save_last", "--precision", "bf16"]
+                "--load_ckpt_path", os.path.join(workdir, "ckpt", "last.ckpt"), "--save_last", "--precision", "bf16",
+                "--native_collator"]              # sample assembly through fsb_bert_collate in this (two-rank) variant
 
     trainer, module = ns["main"](argv(1))
     first = (trainer.global_step, trainer.engine.world, module.model.flat.world_size, module.model.flat.params.float().numpy().copy())
