@@ -143,3 +143,30 @@ def test_t5_recipe_host_flow(launched_with_doubles, tmp_path, monkeypatch):
     hf.install()
     assert transformers.MT5Tokenizer is transformers.T5Tokenizer                # the alias transformers 4.x shipped
     R.t5_recipe(tmp_path, min_drop=None, lr="2e-2")
+
+
+def test_gradient_accumulation_through_the_trainer(launched_with_doubles, tmp_path, monkeypatch):
+    """--accumulate_grad_batches 2 with ZeRO-2 (fp32 shard accumulation in the engine): optimizer steps = micro-batches / 2, the
+    step arithmetic of get_total_steps and the checkpoint's sample counter follow (model_utils.py:194-209)."""
+    import json
+    import runpy
+    import torch
+    F.bert_dir(tmp_path / "m")
+    corpus = F.bert_corpus(tmp_path / "train.json", n=64)
+    monkeypatch.delenv("PL_DEEPSPEED_CONFIG_PATH", raising=False)
+    ns = runpy.run_path(R.EXAMPLE, run_name="example_not_main")
+    trainer, module = ns["main"](["--model_path", str(tmp_path / "m"), "--train_file", str(corpus), "--train_batchsize", "4",
+                                  "--max_seq_length", "64", "--max_epochs", "1", "--accumulate_grad_batches", "2",
+                                  "--learning_rate", "2e-2", "--strategy", "deepspeed_stage_2", "--gradient_clip_val", "1.0",
+                                  "--replace_sampler_ddp", "False", "--dataloader_workers", "0", "--log_every_n_steps", "1",
+                                  "--default_root_dir", str(tmp_path), "--save_ckpt_path", str(tmp_path / "ckpt"),
+                                  "--load_ckpt_path", str(tmp_path / "ckpt" / "last.ckpt"), "--save_last", "--native_collator"])
+    assert module.total_steps == 8 and trainer.global_step == 8               # 64 documents / 4 per micro-batch / 2
+    eng = trainer.engine
+    assert eng.ga_steps == 2 and eng.stage == 2 and eng.acc32 is not None and eng.grad_clip == 1.0
+    assert module.model.loss_scale == 0.5                                       # 1 / (world x GA): the mean over micro-batches
+    state = torch.load(tmp_path / "ckpt" / "last.ckpt" / "checkpoint" / "mp_rank_00_model_states.pt", map_location="cpu",
+                       weights_only=False)
+    assert state["global_step"] == 8 and state["global_samples"] == 64
+    losses = R.losses_of(trainer)
+    assert len(losses) == 8 and losses[-1] < losses[0]
