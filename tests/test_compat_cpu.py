@@ -210,3 +210,43 @@ def test_tp_shard_layout_matches_reference_and_sharded_math_equals_full():
     fm = O.mlp(xin, sd[p + "mlp.w1.weight"], sd[p + "mlp.w3.weight"], sd[p + "mlp.w2.weight"])
     pm = sum(O.mlp(xin, s_[p + "mlp.w1.weight"], s_[p + "mlp.w3.weight"], s_[p + "mlp.w2.weight"]) for s_ in shards)
     assert torch.allclose(pm, fm, atol=1e-5)
+
+
+def _mpu_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fengshen.models.megatron import mpu
+    mpu.initialize_model_parallel(2)
+    t = torch.tensor([float(rank)])
+    dist.all_reduce(t, group=mpu.get_model_parallel_group())
+    d = torch.tensor([float(rank)])
+    dist.all_reduce(d, group=mpu.get_data_parallel_group())
+    q.put((rank, mpu.get_model_parallel_world_size(), mpu.get_model_parallel_rank(), mpu.get_data_parallel_world_size(),
+           mpu.get_data_parallel_rank(), float(t), float(d)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_mpu_groups_tensor_parallel_ranks_consecutive_data_parallel_strided():
+    """mpu/initialize.py:37-118 on 4 gloo ranks with tensor parallelism 2: TP groups {0,1} {2,3}, DP groups {0,2} {1,3}."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mpu_worker, args=(r, 4, 29671, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    try:
+        got = dict((r[0], r[1:]) for r in (q.get(timeout=180) for _ in range(4)))
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.terminate()
+    assert all(p.exitcode == 0 for p in procs)
+    for rank in range(4):
+        tp_world, tp_rank, dp_world, dp_rank, tp_sum, dp_sum = got[rank]
+        assert (tp_world, tp_rank, dp_world, dp_rank) == (2, rank % 2, 2, rank // 2)
+        assert tp_sum == {0: 1.0, 1: 1.0, 2: 5.0, 3: 5.0}[rank]              # 0+1 / 2+3: consecutive ranks share a TP group
+        assert dp_sum == {0: 2.0, 1: 4.0, 2: 2.0, 3: 4.0}[rank]              # 0+2 / 1+3: same TP rank, strided
