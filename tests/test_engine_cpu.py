@@ -214,3 +214,77 @@ def test_compact_grads_folds_layer_buckets_onto_rotating_slots():
     assert [g for g in fb.rot_group if g] == [("layer", 0), ("layer", 1), ("layer", 0)]
     # parameters keep their full-size layout
     assert fb.params.numel() == fb.total
+
+
+# ---- tensor parallelism x data parallelism: the clipping norm sums over BOTH groups, replicated buckets counted once ----------
+def _tp_grads(tp_rank, dp_rank, name, shape):
+    """Shard gradients differ per (tp, dp) rank; the replicated bucket's are the same on both tensor-parallel ranks."""
+    seed = 500 + 10 * dp_rank + (0 if name.startswith("norm") else 1 + tp_rank)
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+
+
+class _TpToy:
+    tp_replicated_buckets = ("norms",)
+
+    def __init__(self, world):
+        s = FlatSpec()
+        s.add("w.weight", (40, 24), "shard")
+        s.add("norm.scale", (24,), "norms")
+        self.flat = FlatBuffers(s, "cpu", world_size=world)
+        self.grad_hook, self.loss_scale = None, 1.0
+
+    def fake_backward(self, tp_rank, dp_rank):
+        if getattr(self, "backward_begin_hook", None):
+            self.backward_begin_hook()
+        for name, bucket in (("w.weight", "shard"), ("norm.scale", "norms")):
+            g = _tp_grads(tp_rank, dp_rank, name, self.flat.offsets[name][1]) * self.loss_scale
+            self.flat.view(name, grad=True).copy_(g.to(torch.bfloat16))
+            self.grad_hook(bucket)
+
+
+def _tp_worker(rank, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=4)
+    sys.path.insert(0, os.path.join(ROOT, "fengshen-lm_b200", "compat"))
+    import cpu_kernels as K
+    from fengshen.models.megatron import mpu
+    from fsb200.engine import ZeroEngine
+    mpu.initialize_model_parallel(2)
+    tp_rank, dp_rank = mpu.get_model_parallel_rank(), mpu.get_data_parallel_rank()
+    model = _TpToy(world=2)
+    eng = ZeroEngine(model, lr=1e-2, grad_clip=0.5, kernels=K, overlap_comm=False, process_group=mpu.get_data_parallel_group(),
+                     tp_group=mpu.get_model_parallel_group())
+    assert eng.world == 2 and eng.tp == 2 and eng.tp_replicated == [True if b[0] == "norms" else False for b in model.flat.buckets]
+    model.fake_backward(tp_rank, dp_rank)
+    eng.backward_done()
+    eng.step()
+    q.put((rank, float(eng.grad_norm), float(eng.coef)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_clipping_norm_under_tensor_parallelism_counts_replicated_buckets_once():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tp_worker, args=(r, 29683, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    try:
+        got = dict((r[0], r[1:]) for r in (q.get(timeout=180) for _ in range(4)))
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.terminate()
+    assert all(p.exitcode == 0 for p in procs)
+    # expectation: the data-parallel mean of the bf16 gradients (wire sum of the two ranks' halves), then
+    # ||g||^2 = sum over tensor-parallel ranks of the shard part + the replicated part ONCE
+    def reduced(tp_rank, name, shape):
+        parts = [(_tp_grads(tp_rank, d, name, shape) * 0.5).to(torch.bfloat16) for d in range(2)]
+        return (parts[0] + parts[1]).float()
+    total = sum(reduced(t, "w.weight", (40, 24)).pow(2).sum() for t in range(2)) + reduced(0, "norm.scale", (24,)).pow(2).sum()
+    want = float(total.sqrt())
+    for rank in range(4):
+        norm, coef = got[rank]
+        assert abs(norm - want) < 1e-4 * want, (rank, norm, want)
+        assert abs(coef - min(1.0, 0.5 / (want + 1e-6))) < 1e-5
